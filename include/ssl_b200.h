@@ -1,0 +1,123 @@
+/*
+ * ssl_b200.h -- C ABI of libssl_b200.so, the sm_100a implementation of the Self-Similarity
+ * Graph (SSG) loss path of ChrisDud0257/SSL.
+ *
+ * Plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in
+ * _host.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Every
+ * entry point returns 0 on success and a non-zero cudaError_t / SSL_B200_E* code otherwise;
+ * ssl_b200_last_error() describes the last failure on the calling thread.  Nothing here
+ * synchronises the device or allocates device memory unless stated.
+ *
+ * Reference interfaces each entry point replaces (paths under the reference checkout,
+ * GAN = GAN-Based-SR/basicsr/losses):
+ *   ssl_b200_compute_similarity            GAN/similarity/similarity.h:2-11   (_compute_similarity)
+ *   ssl_b200_compute_similarity_backward   GAN/similarity/similarity.h:13-23  (_compute_similarity_backward)
+ *   ssl_b200_build_edge_list               GAN/similarity/similaritywrapper.py:64-68 (pad + nonzero),
+ *                                          GAN/../models/realesrganssl_model.py:64-72,385-388 (mask_stride, empty test)
+ *   ssl_b200_ssg_rows_forward              GAN/loss_util.py:231-244 (ssl_cuda) == :182-229 (ssl_pytorch)
+ *   ssl_b200_ssg_rows_backward             autograd of the above + similaritywrapper.py:38-57
+ *   ssl_b200_row_loss                      GAN/basic_loss.py:14-16,41-66 (L1Loss), :269-282 (KLDistanceLoss)
+ *   ssl_b200_laplacian_mask                GAN-Based-SR/scripts/data_preparation/generate_mask.py:22-31
+ */
+#ifndef SSL_B200_H_
+#define SSL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSL_B200_ABI_VERSION 1
+
+/* element types of image tensors */
+#define SSL_B200_F32 0
+#define SSL_B200_BF16 1
+#define SSL_B200_F16 2
+
+/* what a row of the SSG holds */
+#define SSL_B200_ROWS_RAW 0  /* q: raw squared patch distance (similarity.cu output)          */
+#define SSL_B200_ROWS_EXP 1  /* e = exp(-q/(C*kw^2)/sigma)      (generalization=False)        */
+#define SSL_B200_ROWS_NORM 2 /* s = e / (sum e + eps)           (generalization=True)         */
+
+/* error codes beyond cudaError_t */
+#define SSL_B200_EINVAL 10001
+#define SSL_B200_ENOTSUP 10002
+
+int ssl_b200_abi_version(void);
+const char* ssl_b200_last_error(void);
+
+/* ---- drop-in for similarity.h ---------------------------------------------------------- */
+
+/* Raw patch distance, reference calling convention: `image` is the REFLECT-PADDED fp32 image
+ * [channel, height, width] (height/width are padded sizes), `pos` is int32 [mc,2] (row, col) in
+ * padded coordinates, `out` is [mc, psize, psize].  The reference accumulates into a
+ * zero-initialised `out`; this implementation overwrites it (same result under that contract). */
+int ssl_b200_compute_similarity(const float* image, const int32_t* pos, float* out, int mc, int psize,
+                                int ksize, int height, int width, int channel, void* stream);
+
+/* Backward of the above: `grads` is dL/d out [mc,psize,psize]; contributions are ADDED into
+ * `image_grads` [channel,height,width] (caller zeroes it, as similaritywrapper.py:47 does). */
+int ssl_b200_compute_similarity_backward(const float* image, const float* grads, const int32_t* pos,
+                                         float* image_grads, int mc, int psize, int ksize, int height,
+                                         int width, int channel, void* stream);
+
+/* ---- batched path ---------------------------------------------------------------------- */
+
+/* Bytes of scratch ssl_b200_build_edge_list needs for n_pixels = B*H*W mask pixels. */
+size_t ssl_b200_edge_list_workspace_bytes(int64_t n_pixels);
+
+/* Edge list of a batch, with no host round trip.
+ *   mask          float [B, mask_channels, H, W]; channel 0 is read; a pixel is an edge iff its
+ *                 value == 1.0f exactly and (mask_stride <= 1 or y % mask_stride == x % mask_stride)
+ *   edges         int32 [capacity]: flat index b*H*W + y*W + x of each edge pixel, ascending
+ *                 (= images in order, row-major inside an image: the reference's row order)
+ *   counts        int32 [2 + B]: counts[0] = number of edges written (min(total, capacity)),
+ *                 counts[1] = total found, counts[2+b] = edges of image b
+ */
+int ssl_b200_build_edge_list(const float* mask, int B, int mask_channels, int H, int W, int mask_stride,
+                             int32_t* edges, int capacity, int32_t* counts, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* SSG rows of every listed edge pixel.  image: [B,C,H,W] of `dtype` (unpadded; the reflect pad of
+ * loss_util.py:189-191 is applied by index mapping).  n_edges_dev points at the device count
+ * (counts[0] above); max_edges bounds the grid and the rows buffer.  rows: fp32 [max_edges, ks*ks].
+ * image2/rows2 may name a second image of the same shape processed in the same launch (NULL = none). */
+int ssl_b200_ssg_rows_forward(const void* image, const void* image2, int dtype, int B, int C, int H, int W,
+                              const int32_t* edges, const int32_t* n_edges_dev, int max_edges, int ks, int kw,
+                              float sigma, float eps, int rows_mode, float* rows, float* rows2, void* stream);
+
+/* In place: rows (as written by the forward in `rows_mode`) and grad_rows = dL/drows  ->
+ * grad_rows = dL/dq (raw distance).  Chain of loss_util.py:234-243. */
+int ssl_b200_rows_grad_to_distance_grad(const float* rows, float* grad_rows, const int32_t* n_edges_dev,
+                                        int max_edges, int ks, int kw, int C, float sigma, int rows_mode,
+                                        void* stream);
+
+/* dL/dimage accumulated (fp32, [B,C,H,W], caller zeroes) from gq = dL/dq rows, including the
+ * adjoint of the reflect pad. */
+int ssl_b200_ssg_rows_backward(const void* image, int dtype, int B, int C, int H, int W, const int32_t* edges,
+                               const int32_t* n_edges_dev, int max_edges, int ks, int kw, const float* gq,
+                               float* grad_image, void* stream);
+
+/* Row loss between SR rows s and GT rows t (both ROWS_EXP or ROWS_NORM):
+ *   sums[0] += sum |s - t|                          (L1Loss numerator)
+ *   sums[1] += sum t' (log t' - log s'),  x' = max(x, 1e-10)   (KLDistanceLoss numerator)
+ * and, when gq != NULL, gq = dL/dq_sr for  L = w_l1 * sums[0] + w_kl * sums[1]  (the 1/N of the
+ * 'mean' reduction is applied by the caller once the global count is known).
+ * sums: double [2], ACCUMULATED (caller zeroes); scratch: double [2 * ssl_b200_row_loss_blocks()]. */
+int ssl_b200_row_loss_blocks(void);
+int ssl_b200_row_loss(const float* rows_sr, const float* rows_gt, const int32_t* n_edges_dev, int max_edges,
+                      int ks, int kw, int C, float sigma, int rows_mode, float w_l1, float w_kl, float* gq,
+                      double* sums, double* scratch, void* stream);
+
+/* Edge mask of generate_mask.py on the GT crop: luma of round(255*clamp(gt,0,1)), 4-neighbour
+ * Laplacian with BORDER_REFLECT_101 saturated to [0,255], mask = lap > threshold.
+ * gt: [B,3,H,W] of `dtype`; mask: float [B,1,H,W]. */
+int ssl_b200_laplacian_mask(const void* gt, int dtype, int B, int H, int W, float threshold, float* mask,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSL_B200_H_ */

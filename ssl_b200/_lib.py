@@ -1,0 +1,84 @@
+"""ctypes binding of libssl_b200.so (the C ABI of include/ssl_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails, this module
+raises.  Build it with ``python -m ssl_b200.csrc.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libssl_b200.so")
+
+F32, BF16, F16 = 0, 1, 2
+ROWS_RAW, ROWS_EXP, ROWS_NORM = 0, 1, 2
+ABI_VERSION = 1
+
+_c_int, _c_float, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/ssl_b200.h one to one
+SIGNATURES = {
+    "ssl_b200_abi_version": (_c_int, []),
+    "ssl_b200_last_error": (ctypes.c_char_p, []),
+    "ssl_b200_compute_similarity": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                             _c_int, _c_void_p]),
+    "ssl_b200_compute_similarity_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                                                      _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "ssl_b200_edge_list_workspace_bytes": (_c_size_t, [ctypes.c_int64]),
+    "ssl_b200_build_edge_list": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int,
+                                          _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "ssl_b200_ssg_rows_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                           _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_void_p,
+                                           _c_void_p, _c_void_p]),
+    "ssl_b200_rows_grad_to_distance_grad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
+                                                     _c_float, _c_int, _c_void_p]),
+    "ssl_b200_ssg_rows_backward": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
+                                            _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "ssl_b200_row_loss_blocks": (_c_int, []),
+    "ssl_b200_row_loss": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int,
+                                   _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ssl_b200_laplacian_mask": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p]),
+}
+
+_lib = None
+
+
+class SSLB200Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SSLB200Error(
+            f"{LIB_PATH} is missing: build the sm_100a kernels with `python -m ssl_b200.csrc.build`. "
+            "ssl_b200 has no CPU / PyTorch fallback path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.ssl_b200_abi_version() != ABI_VERSION:
+        raise SSLB200Error(f"libssl_b200.so ABI {lib.ssl_b200_abi_version()} != binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.ssl_b200_last_error()
+        raise SSLB200Error(f"{name} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def dtype_code(dtype) -> int:
+    import torch
+    try:
+        return {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}[dtype]
+    except KeyError:
+        raise TypeError(f"ssl_b200 kernels take float32 / bfloat16 / float16 images, got {dtype}") from None

@@ -1,0 +1,149 @@
+// Shared helpers for the ssl_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ssl_b200.h"
+
+namespace sslb {
+
+// ---- host-side error plumbing -------------------------------------------------------------
+inline char* err_buf() {
+    static thread_local char buf[512] = "";
+    return buf;
+}
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+#define SSLB_REQUIRE(cond, ...)                                   \
+    do {                                                          \
+        if (!(cond)) return sslb::fail(SSL_B200_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+#define SSLB_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) return sslb::fail((int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int max_smem_optin = 0;
+};
+
+inline int device_info(DeviceInfo* out) {
+    static thread_local int cached_dev = -1;
+    static thread_local DeviceInfo cached;
+    int dev = 0;
+    SSLB_CUDA(cudaGetDevice(&dev));
+    if (dev != cached_dev) {
+        SSLB_CUDA(cudaDeviceGetAttribute(&cached.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        SSLB_CUDA(cudaDeviceGetAttribute(&cached.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cached_dev = dev;
+    }
+    *out = cached;
+    return 0;
+}
+
+// ---- device helpers -----------------------------------------------------------------------
+
+// F.pad(mode="reflect") index map: padded coordinate -> source coordinate (no edge repeat).
+__device__ __forceinline__ int reflect_idx(int v, int n) {
+    v = v < 0 ? -v : v;
+    return v > n - 1 ? 2 * (n - 1) - v : v;
+}
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) {
+    return __ldg(p);
+}
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __bfloat162float(__ldg(p));
+}
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p) {
+    return __half2float(__ldg(p));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum with a fixed reduction tree (deterministic).  `red` holds >= 32 elements.
+// Every thread gets the total.  Contains two __syncthreads().
+template <typename V>
+__device__ __forceinline__ V block_sum(V v, V* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` from a previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    V t = lane < nwarp ? red[lane] : V(0);
+    return warp_sum(t);
+}
+
+// Where an edge pixel is.  Either the batched flat list (b*H*W + y*W + x) or the reference's
+// int32 [mc,2] (row, col) list of similaritywrapper.py:67 (single image).
+struct EdgeRef {
+    const int32_t* flat;
+    const int32_t* yx;
+};
+
+__device__ __forceinline__ void decode_edge(const EdgeRef& e, int n, int H, int W, int& b, int& y, int& x) {
+    if (e.yx) {
+        b = 0;
+        y = e.yx[2 * n];
+        x = e.yx[2 * n + 1];
+    } else {
+        const int f = e.flat[n];
+        const int hw = H * W;
+        b = f / hw;
+        const int r = f - b * hw;
+        y = r / W;
+        x = r - y * W;
+    }
+}
+
+__device__ __forceinline__ int edge_count(const int32_t* n_dev, int max_edges) {
+    if (!n_dev) return max_edges;
+    const int n = *n_dev;
+    return n < max_edges ? n : max_edges;
+}
+
+}  // namespace sslb
+
+#define SSLB_DISPATCH_DTYPE(dtype, T, ...)                                          \
+    switch (dtype) {                                                                \
+        case SSL_B200_F32: { using T = float; __VA_ARGS__; break; }                  \
+        case SSL_B200_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }         \
+        case SSL_B200_F16: { using T = __half; __VA_ARGS__; break; }                 \
+        default: return sslb::fail(SSL_B200_EINVAL, "unknown dtype %d", (int)(dtype)); \
+    }

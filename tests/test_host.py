@@ -1,0 +1,109 @@
+"""CPU-side checks: the C ABI library loads and exports what include/ssl_b200.h declares, the host
+logic (argument validation, sharding, the (sum,count) reduction under gloo) and the synthetic data."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ssl_b200 import _lib
+    from ssl_b200.csrc import build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "ssl_b200.h")).read()
+    declared = set(re.findall(r"\b(ssl_b200_\w+)\s*\(", header))
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in ssl_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "python binding and header out of sync"
+    assert _lib.load().ssl_b200_abi_version() == _lib.ABI_VERSION
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = __import__("ssl_b200")._lib
+    l = lib.load()
+    null = ctypes.c_void_p(0)
+    rc = l.ssl_b200_compute_similarity(null, null, null, 1, 25, 9, 64, 64, 3, null)
+    assert rc == 10001 and b"null" in l.ssl_b200_last_error()
+    one = ctypes.c_void_p(8)
+    rc = l.ssl_b200_ssg_rows_forward(one, null, 0, 1, 3, 64, 64, one, null, 0, 24, 9, 0.004, 1e-10, 2, one, null, null)
+    assert rc == 10001 and b"odd" in l.ssl_b200_last_error()
+    rc = l.ssl_b200_ssg_rows_forward(one, null, 0, 1, 3, 8, 8, one, null, 0, 25, 9, 0.004, 1e-10, 2, one, null, null)
+    assert rc == 10001 and b"reflect" in l.ssl_b200_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ssl_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle|libssg_oracle|oracle/|ssl_oracle", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(text), f"{f} reaches into the oracle"
+
+
+def test_cpu_tensor_is_rejected_not_emulated():
+    import ssl_b200
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ssl_b200.ssl(torch.zeros(1, 3, 32, 32), torch.zeros(1, 3, 32, 32), torch.ones(1, 1, 32, 32), 11, 5)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ssl_b200.build_edge_list(torch.ones(1, 1, 8, 8))
+    with pytest.raises(ValueError):
+        ssl_b200.similarity_map(img=torch.zeros(1, 3, 32, 32), mask=torch.ones(1, 1, 32, 32), ssl_mode="nope")
+
+
+def test_shard_range_and_mean_from_terms():
+    from ssl_b200.dist import mean_from_terms, shard_range
+    assert list(shard_range(64, 3, 8)) == list(range(24, 32))
+    with pytest.raises(ValueError):
+        shard_range(10, 0, 4)
+    t = torch.tensor([6.25, 12.5, 2.0], dtype=torch.float64)
+    assert float(mean_from_terms(t, 625, 1.0, 0.5)) == pytest.approx(6.25 / 1250 + 0.5 * 12.5 / 1250)
+    assert float(mean_from_terms(torch.zeros(3, dtype=torch.float64), 625)) == 0.0
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssl_b200.dist import make_reducer, mean_from_terms
+    local = torch.tensor([1.0 + rank, 10.0 * (rank + 1), 3.0 + 2 * rank], dtype=torch.float64)
+    red = make_reducer("global")
+    glob = red(local)
+    ddp = make_reducer("ddp")
+    out[rank] = (glob.tolist(), ddp is None, float(mean_from_terms(glob, 4)))
+    dist.destroy_process_group()
+
+
+def test_global_parity_reduction_world2_gloo():
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+        res = dict(out)
+    for r in (0, 1):
+        terms, ddp_none, mean = res[r]
+        assert terms == [3.0, 30.0, 8.0]       # sums and row counts add across ranks
+        assert ddp_none                        # reference DDP semantics: no collective
+        assert mean == pytest.approx(3.0 / 32)  # normalised by the GLOBAL element count
+
+
+def test_synth_is_deterministic_and_nondegenerate():
+    from ssl_b200 import synth
+    a = synth.make_case(2, 64, 64, seed=5)
+    b = synth.make_case(2, 64, 64, seed=5)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    sr, gt, mask = a
+    assert 0.0 <= float(gt.min()) and float(gt.max()) <= 1.0
+    assert float((sr - gt).abs().mean()) > 1e-3
+    assert mask[:, :, 0, 0].all() and mask[:, :, -1, -1].all()
+    assert 0.05 < float(mask.mean()) < 0.2
