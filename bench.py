@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the SSG loss hot path (BASELINE.json metric: edge-pixels/sec, SSG fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the whole SSL block (edge list, SSG rows of SR and GT, L1, backward into
+SR) over one batch of synthetic crops.  Workload = BASELINE.json configs[1]: batch 16 of 256x256
+fp32 crops, k_search=25, k_window=9, sigma=0.004, Bernoulli(0.114) edge mask, per GPU
+(weak scaling: rank r owns its own 16 crops, seed 1+r; the only exchange is the 24-byte all-reduce
+of [sum|d|, sumKL, n_rows] at the end of the forward).
+
+Reported on ONE JSON line (rank 0):
+  value      edge-px/s with inputs resident in HBM, CUDA-event timed per step, max over ranks;
+             L2 is flushed (256 MiB write) between timed steps, outside the timed events
+  e2e        the same metric through the C ABI's host entry (ssl_b200_loss_step_host): pinned host
+             sr/gt/mask -> device, step, loss + gradient -> host, all inside the timed region
+  roofline   dominant kernel: algorithmic bytes per launch / its CUDA-event duration vs the
+             measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle's restatement of the reference ssl_pytorch (oracle/ssl_oracle.py) timed on
+             this box's host cores on a bounded sample of the same workload
+`--impl reference` times that CPU restatement as the whole run (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KS, KW, SIGMA, EPS = 25, 9, 0.004, 1e-10
+BATCH_PER_GPU, HEIGHT, WIDTH, DENSITY = 16, 256, 256, 0.114
+L = KS * KS
+# algorithmic HBM reads per edge pixel, fp32: three search-tile gathers of
+# C*k_s^2*4 = 7,500 B (SR fwd, GT fwd, SR bwd) + 8 B position = 22,508 B
+TILE_BYTES = 3 * L * 4
+ALGO_BYTES_STEP = 3 * TILE_BYTES + 8
+ALGO_BYTES_FWD = 2 * TILE_BYTES + 8      # the forward launch gathers the SR and the GT tile
+ALGO_BYTES_BWD = TILE_BYTES              # the backward launch gathers the SR tile again
+FALLBACK_HBM_GBS = 6650.0                # B200_PROFILING.md fallback
+
+
+def baseline_metric():
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as f:
+            return json.load(f)["metric"]
+    except Exception:
+        return "edge-pixels/sec SSG fwd+bwd, 256×256 k_s=25 k_w=9, 1/2/4/8 B200"
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: batch=16 256x256 fp32 crops per GPU, k_search=25 k_window=9 sigma=0.004, "
+                        "Bernoulli(0.114) edge mask (~7.5k edge px per crop), fwd(SR)+fwd(GT)+L1+bwd",
+            "global_batch": BATCH_PER_GPU * n_gpus, "crop": [HEIGHT, WIDTH], "k_search": KS, "k_window": KW,
+            "mask_density": DENSITY, "parallelism": f"dp{n_gpus} (images sharded, 24-byte all-reduce)",
+            "l2": "flushed between timed steps (256 MiB write, outside the timed events)"}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while a region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if visible:
+                index = int(visible.split(",")[index]) if visible.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.ok:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference ssl_pytorch
+# ---------------------------------------------------------------------------------------------
+
+def cpu_sample(n_px, seed=1):
+    """A bounded sample of the workload: the first crop of the config-2 batch, with the mask cut to
+    the first row bands that hold ~n_px edge pixels."""
+    import torch
+    from ssl_b200 import synth
+    sr, gt, mask = synth.make_case(1, HEIGHT, WIDTH, seed=seed, density=DENSITY)
+    per_row = mask[0, 0].sum(dim=1).cumsum(0)
+    rows = int((per_row < n_px).sum().item()) + 1
+    m = torch.zeros_like(mask)
+    m[:, :, :rows] = mask[:, :, :rows]
+    return sr, gt, m, int(m.sum().item())
+
+
+def cpu_step(sr, gt, mask):
+    from oracle import ssl_oracle
+    t0 = time.perf_counter()
+    loss, grad, n = ssl_oracle.ssl_step_pytorch_port(sr, gt, mask, KS, KW, SIGMA, True, EPS, 1.0, max_px=512)
+    return time.perf_counter() - t0, n
+
+
+def cpu_baseline(budget_s=15.0):
+    """Edge-px/s of the CPU restatement on ~budget_s seconds of work."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    sr, gt, m, n = cpu_sample(256)
+    dt, _ = cpu_step(sr, gt, m)          # warm-up + calibration
+    rate = n / dt
+    n_px = int(min(max(rate * budget_s, 256), 16384))
+    sr, gt, m, n = cpu_sample(n_px)
+    dt, _ = cpu_step(sr, gt, m)
+    return {"value": n / dt, "unit": "edge-pixels/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} edge px of crop 0 of the workload (first row bands), fwd(SR)+fwd(GT)+L1+bwd with "
+                      f"oracle.ssl_step_pytorch_port (restated ssl_pytorch, 512-px chunks), {dt:.1f} s wall, "
+                      f"{os.cpu_count()} host cpus"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    sr, gt, m, n = cpu_sample(128)
+    dt, _ = cpu_step(sr, gt, m)
+    rate = n / dt
+    total_steps = args.steps + args.warmup
+    n_px = int(min(max(rate * 120.0 / max(total_steps, 1), 64), 4096))
+    sr, gt, m, n = cpu_sample(n_px)
+    for _ in range(args.warmup):
+        cpu_step(sr, gt, m)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_step(sr, gt, m)
+        t += dt
+    value = n * args.steps / t
+    sample = (f"each step = {n} edge px of crop 0 of the workload (first row bands), fwd(SR)+fwd(GT)+L1+bwd, "
+              f"oracle.ssl_step_pytorch_port (op-for-op restatement of the reference ssl_pytorch; the reference "
+              f"itself is Python under /root/reference and does not travel to the GPU box)")
+    out = {"impl": "reference", "metric": baseline_metric(), "value": value, "unit": "edge-pixels/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args.gpus),
+           "cpu_baseline": {"value": value, "unit": "edge-pixels/s", "cores": torch.get_num_threads(),
+                            "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "edge-pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU path; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import ssl_b200
+    from ssl_b200 import _lib, synth
+    from ssl_b200 import functional as F_
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    sr_h, gt_h, mask_h = synth.make_case(BATCH_PER_GPU, HEIGHT, WIDTH, seed=1 + rank, density=DENSITY)
+    sr_h, gt_h, mask_h = sr_h.pin_memory(), gt_h.pin_memory(), mask_h.pin_memory()
+    sr_d, gt_d, mask_d = sr_h.to(dev), gt_h.to(dev), mask_h.to(dev)
+    n_edges = int(mask_h.sum().item())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        x = sr_d.detach().requires_grad_(True)
+        loss = ssl_b200.ssl(x, gt_d, mask_d, KS, KW, SIGMA, True, EPS, loss_weight=1.0, parity="global")
+        loss.backward()
+        return loss, x.grad
+
+    def timed_steps(fn, k, w):
+        for _ in range(w):
+            fn()
+        evs = []
+        barrier()
+        for _ in range(k):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------
+    with ClockSampler(local) as clocks:
+        launches0 = lib.ssl_b200_launch_count()
+        t_local = timed_steps(step, args.steps, args.warmup)
+        launches = lib.ssl_b200_launch_count() - launches0
+    # warm-up launches are inside that delta: keep the timed share only
+    launches = launches * args.steps // max(args.steps + args.warmup, 1)
+    t_step = max_over_ranks(t_local)
+    total_edges = sum_over_ranks(float(n_edges))
+    value = total_edges * args.steps / t_step
+    total_launches = int(sum_over_ranks(float(launches)))
+
+    # ---- e2e: host buffers through the C ABI --------------------------------------------------
+    grad_h = torch.empty_like(sr_h).pin_memory()
+
+    def host_step():
+        return ssl_b200.ssl_step_host(sr_h, gt_h, mask_h, KS, KW, SIGMA, True, EPS, 1.0, out_grad=grad_h)
+
+    for _ in range(max(args.warmup, 3)):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    torch.cuda.synchronize()
+    t_host = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": total_edges * args.steps / t_host, "unit": "edge-pixels/s",
+           "h2d_bytes_per_step": int(world * (sr_h.numel() + gt_h.numel() + mask_h.numel()) * 4),
+           "d2h_bytes_per_step": int(world * (grad_h.numel() * 4 + 12 + 8)),
+           "ms_per_step": 1e3 * t_host / args.steps,
+           "call": "ssl_b200_loss_step_host (pinned host sr/gt/mask in, loss[3] + d loss/d sr out, wall clock)"}
+
+    # ---- roofline of the dominant kernel (rank 0's GPU, timed alone on the launching stream) ---
+    roof = None
+    kernels = {}
+    if rank == 0:
+        el = ssl_b200.build_edge_list(mask_d)
+        n = el.count()
+        rows_a = torch.empty(n, L, dtype=torch.float32, device=dev)
+        rows_b = torch.empty_like(rows_a)
+        grad = torch.zeros_like(sr_d)
+        gq = torch.randn(n, L, device=dev) * 1e-6
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def k_fwd():
+            _lib.call("ssl_b200_ssg_rows_forward", vp(sr_d), vp(gt_d), _lib.F32, BATCH_PER_GPU, 3, HEIGHT, WIDTH,
+                      vp(el.edges), vp(el.counts), n, KS, KW, SIGMA, EPS, _lib.ROWS_NORM, vp(rows_a), vp(rows_b), st())
+
+        def k_bwd():
+            _lib.call("ssl_b200_ssg_rows_backward", vp(sr_d), _lib.F32, BATCH_PER_GPU, 3, HEIGHT, WIDTH, vp(el.edges),
+                      vp(el.counts), n, KS, KW, vp(gq), vp(grad), st())
+
+        def time_kernel(fn, k):
+            for _ in range(3):
+                fn()
+            tot = 0.0
+            for _ in range(k):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            return tot / k * 1e-3
+
+        k = min(args.steps, 10)
+        t_fwd, t_bwd = time_kernel(k_fwd, k), time_kernel(k_bwd, k)
+        peak, peak_src = hbm_peak()
+        kernels = {"ssg_rows_forward(SR+GT)": {"ms": 1e3 * t_fwd, "algo_gbs": n * ALGO_BYTES_FWD / t_fwd / 1e9},
+                   "ssg_rows_backward(SR)": {"ms": 1e3 * t_bwd, "algo_gbs": n * ALGO_BYTES_BWD / t_bwd / 1e9}}
+        name, t_dom, per_px = (("ssg_rows_forward(SR+GT)", t_fwd, ALGO_BYTES_FWD) if t_fwd >= t_bwd else
+                               ("ssg_rows_backward(SR)", t_bwd, ALGO_BYTES_BWD))
+        achieved = n * per_px / t_dom / 1e9
+        step_gbs = n_edges * ALGO_BYTES_STEP / (t_local / args.steps) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": name, "kernel_ms": 1e3 * t_dom, "peak_source": peak_src,
+                "algorithmic_bytes_per_edge_px": per_px,
+                "step": {"achieved": step_gbs, "frac": step_gbs / peak,
+                         "algorithmic_bytes_per_edge_px": ALGO_BYTES_STEP,
+                         "note": "whole fwd+bwd step (the figure north_star's 70% target is stated on)"}}
+        traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                with open(traffic_file) as f:
+                    roof["traffic"] = json.load(f).get(name)
+            except Exception:
+                pass
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        out = {"metric": baseline_metric(), "value": value, "unit": "edge-pixels/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": workload_config(world), "edge_px_per_step": int(total_edges),
+               "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+               "gpu_launches": total_launches, "clocks": clocks.summary()}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun
+            import subprocess
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+                   os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
+                   str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+            raise SystemExit(subprocess.call(cmd))
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

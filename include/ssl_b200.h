@@ -17,6 +17,9 @@
  *   ssl_b200_ssg_rows_forward              GAN/loss_util.py:231-244 (ssl_cuda) == :182-229 (ssl_pytorch)
  *   ssl_b200_ssg_rows_backward             autograd of the above + similaritywrapper.py:38-57
  *   ssl_b200_row_loss                      GAN/basic_loss.py:14-16,41-66 (L1Loss), :269-282 (KLDistanceLoss)
+ *   ssl_b200_loss_forward_backward,        GAN/../models/realesrganssl_model.py:378-430 (the SSL block of train_net_g;
+ *   ssl_b200_loss_step_host                same block in 7 other *ssl_model.py, train_BSGRAN/models/model_ssl.py:285-334,
+ *                                          Diffusion-Based-SR/ldm/models/diffusion/ddpmssl.py:438-513)
  *   ssl_b200_laplacian_mask                GAN-Based-SR/scripts/data_preparation/generate_mask.py:22-31
  */
 #ifndef SSL_B200_H_
@@ -110,6 +113,39 @@ int ssl_b200_row_loss_blocks(void);
 int ssl_b200_row_loss(const float* rows_sr, const float* rows_gt, const int32_t* n_edges_dev, int max_edges,
                       int ks, int kw, int C, float sigma, int rows_mode, float w_l1, float w_kl, float* gq,
                       double* sums, double* scratch, void* stream);
+
+/* ---- whole step ------------------------------------------------------------------------- */
+
+/* The reference training-step block (realesrganssl_model.py:378-430: per-image loop, two
+ * similarity_map calls, cat, L1Loss [+ KLDistanceLoss], and its backward) for a batch whose edge
+ * list is already built (ssl_b200_build_edge_list; counts[0] is read on the device).
+ *   sr, gt       [B,C,H,W] of `dtype`
+ *   grad_sr      fp32 [B,C,H,W] or NULL: OVERWRITTEN with d(w_l1*sum|d| + w_kl*sumKL)/d sr, i.e.
+ *                the gradient before the 1/N of the 'mean' reduction (N = n_rows*ks*ks is only
+ *                known once the counts of all ranks are: the caller scales)
+ *   terms        double [3], OVERWRITTEN: sum|S_sr - S_gt|, sum KL, n_rows
+ *   workspace    ssl_b200_loss_workspace_bytes(ks, max_edges) bytes of scratch (rows never leave it) */
+size_t ssl_b200_loss_workspace_bytes(int ks, int max_edges);
+int ssl_b200_loss_forward_backward(const void* sr, const void* gt, int dtype, int B, int C, int H, int W,
+                                   const int32_t* edges, const int32_t* counts, int max_edges, int ks, int kw,
+                                   float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* grad_sr,
+                                   double* terms, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same step on HOST buffers (the end-to-end call of a host-side plugin): copies sr/gt/mask to the
+ * device, builds the edge list, runs the step, applies the 'mean' (single device: N is local) and
+ * copies the results back.  fp32 images.  loss_host: float [3] = total, w_l1*L1, w_kl*KL;
+ * grad_host: fp32 [B,C,H,W] = d total / d sr, or NULL.  n_rows_host: int64 [1] or NULL.
+ * ALLOCATES (and caches per device) its device arena; SYNCHRONISES `stream` before returning.
+ * Pinned host buffers make the copies asynchronous with respect to each other. */
+int ssl_b200_loss_step_host(const float* sr_host, const float* gt_host, const float* mask_host, int mask_channels,
+                            int B, int C, int H, int W, int mask_stride, int ks, int kw, float sigma, float eps,
+                            int rows_mode, float w_l1, float w_kl, float* loss_host, float* grad_host,
+                            int64_t* n_rows_host, void* stream);
+/* Frees the cached arena of the current device. */
+int ssl_b200_release_host_arena(void);
+
+/* Number of kernels this library has launched in this process so far (all threads). */
+uint64_t ssl_b200_launch_count(void);
 
 /* Edge mask of generate_mask.py on the GT crop: luma of round(255*clamp(gt,0,1)), 4-neighbour
  * Laplacian with BORDER_REFLECT_101 saturated to [0,255], mask = lap > threshold.

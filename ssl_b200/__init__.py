@@ -5,13 +5,15 @@ Public surface:
     similarity_map                   drop-in for basicsr.losses.loss_util.similarity_map
     compute_similarity               drop-in for basicsr.losses.similarity.similaritywrapper.compute_similarity
     build_edge_list, ssg_rows, laplacian_mask   the pieces
+    ssl_step_host                    the same step on host buffers (H2D + step + D2H in one C-ABI call)
 Importing the package does not need a GPU; calling any operator without CUDA tensors or without
 the built library raises (there is no fallback path).
 """
 from .compat import similarity_map
-from .functional import EdgeList, build_edge_list, compute_similarity, laplacian_mask, ssg_rows
+from .functional import (EdgeList, build_edge_list, compute_similarity, laplacian_mask, ssg_rows,
+                         ssl_step_host)
 from .loss import SelfSimilarityLoss, ssl
 
 __all__ = ["SelfSimilarityLoss", "ssl", "similarity_map", "compute_similarity", "build_edge_list", "ssg_rows",
-           "laplacian_mask", "EdgeList"]
+           "laplacian_mask", "EdgeList", "ssl_step_host"]
 __version__ = "0.1.0"

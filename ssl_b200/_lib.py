@@ -38,6 +38,16 @@ SIGNATURES = {
     "ssl_b200_row_loss_blocks": (_c_int, []),
     "ssl_b200_row_loss": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int,
                                    _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ssl_b200_loss_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+    "ssl_b200_loss_forward_backward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                                _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_float,
+                                                _c_int, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p,
+                                                _c_size_t, _c_void_p]),
+    "ssl_b200_loss_step_host": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                         _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_float, _c_float,
+                                         _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ssl_b200_release_host_arena": (_c_int, []),
+    "ssl_b200_launch_count": (ctypes.c_uint64, []),
     "ssl_b200_laplacian_mask": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p]),
 }
 

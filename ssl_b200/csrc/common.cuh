@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "ssl_b200.h"
 
 namespace sslb {
@@ -26,7 +28,14 @@ inline int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-inline int check_launch(const char* what) {
+// Kernels launched by this library (ssl_b200_launch_count); bumped at every launch site.
+inline std::atomic<uint64_t>& launch_counter() {
+    static std::atomic<uint64_t> n{0};
+    return n;
+}
+
+inline int check_launch(const char* what, int n_kernels = 1) {
+    launch_counter().fetch_add((uint64_t)n_kernels, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
     return 0;

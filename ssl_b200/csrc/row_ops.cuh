@@ -20,6 +20,22 @@ struct RowLossParams {
     double* scratch;  // [2 * gridDim.x]
 };
 
+// One element of KLDistanceLoss (basic_loss.py:269-282), t (log t - log s), in a form that does not
+// cancel: with r = (t - s)/s,
+//     t log(t/s) = [ s r^2 + t (log1p(r) - r) ] + (t - s).
+// The bracket is >= 0 and second-order small when s ~ t, so it is summed as is; the (t - s) parts
+// sum to zero over a normalised row up to the 1e-10 clamps, which the caller adds back exactly.
+// (Plain logf(t) - logf(s) loses ~1e-7*|log t| / |r| relative accuracy per term.)
+__device__ __forceinline__ float kl_term(float sc, float tc) {
+    const float r = (tc - sc) / sc;
+    if (fabsf(r) < 0.125f) {
+        const float h = r * r * (-0.5f + r * (0.33333334f + r * (-0.25f + r * (0.2f + r * (-0.16666667f +
+                        r * (0.14285715f + r * (-0.125f + r * 0.11111111f)))))));
+        return fmaf(sc * r, r, tc * h);
+    }
+    return tc * log1pf(r) - (tc - sc);
+}
+
 // L1Loss (basic_loss.py:14-16,59-66) and KLDistanceLoss (basic_loss.py:269-282) numerators of a
 // block's rows, plus dL/dq of the SR rows:
 //   g_s   = w_l1 * sign(s - t) + w_kl * d/ds[ t' (log t' - log s') ],  x' = max(x, 1e-10)
@@ -41,7 +57,8 @@ __global__ void __launch_bounds__(kRowThreads) row_loss_kernel(RowLossParams p) 
             float g = p.w_l1 * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
             if (p.w_kl != 0.f) {
                 const float sc = fmaxf(sv, 1e-10f), tc = fmaxf(tv, 1e-10f);
-                kl += tc * (logf(tc) - logf(sc));
+                // NORM rows sum to one, so sum(t - s) is zero up to the clamps; EXP rows carry it
+                kl += kl_term(sc, tc) + (p.mode == SSL_B200_ROWS_NORM ? ((tc - tv) - (sc - sv)) : (tc - sc));
                 if (sv > 1e-10f) g -= p.w_kl * tc / sc;
             }
             dot = fmaf(g, sv, dot);

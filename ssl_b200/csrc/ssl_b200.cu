@@ -144,7 +144,7 @@ extern "C" int ssl_b200_build_edge_list(const float* mask, int B, int mask_chann
     edge_count_kernel<<<p.n_chunks, kElThreads, 0, st>>>(p);
     edge_scan_kernel<<<1, 1024, 0, st>>>(p);
     edge_emit_kernel<<<p.n_chunks, kElThreads, 0, st>>>(p);
-    return check_launch("build_edge_list");
+    return check_launch("build_edge_list", 3);
 }
 
 extern "C" int ssl_b200_ssg_rows_forward(const void* image, const void* image2, int dtype, int B, int C, int H, int W,
@@ -224,7 +224,7 @@ extern "C" int ssl_b200_row_loss(const float* rows_sr, const float* rows_gt, con
     cudaStream_t st = (cudaStream_t)stream;
     row_loss_kernel<<<blocks, kRowThreads, 0, st>>>(p);
     row_loss_finalize_kernel<<<1, 32, 0, st>>>(scratch, blocks, sums);
-    return check_launch("row_loss");
+    return check_launch("row_loss", 2);
 }
 
 extern "C" int ssl_b200_laplacian_mask(const void* gt, int dtype, int B, int H, int W, float threshold, float* mask,
@@ -239,3 +239,193 @@ extern "C" int ssl_b200_laplacian_mask(const void* gt, int dtype, int B, int H, 
     });
     return check_launch("laplacian_mask");
 }
+
+// ---- whole step ---------------------------------------------------------------------------
+
+namespace {
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// [terms: sum|d|, sumKL, n_rows] -> loss[0..2] = total, w_l1*L1, w_kl*KL and inv_n = 1/(n_rows*L)
+__global__ void finalize_loss_kernel(const double* terms, int L, float w_l1, float w_kl, float* loss, float* inv_n) {
+    const double n_tot = fmax(terms[2] * (double)L, 1.0);
+    const double l1 = (double)w_l1 * terms[0] / n_tot, kl = (double)w_kl * terms[1] / n_tot;
+    loss[0] = (float)(l1 + kl);
+    loss[1] = (float)l1;
+    loss[2] = (float)kl;
+    *inv_n = (float)(1.0 / n_tot);
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(float4* g, long long n4, const float* scale) {
+    const float s = *scale;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = g[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        g[i] = v;
+    }
+}
+
+__global__ void set_terms_count_kernel(const int32_t* counts, double* terms) { terms[2] = (double)counts[0]; }
+
+}  // namespace
+
+extern "C" size_t ssl_b200_loss_workspace_bytes(int ks, int max_edges) {
+    const size_t rows = align256((size_t)(max_edges > 0 ? max_edges : 1) * ks * ks * sizeof(float));
+    return 2 * rows + align256(2 * sizeof(double) * (size_t)ssl_b200_row_loss_blocks());
+}
+
+extern "C" int ssl_b200_loss_forward_backward(const void* sr, const void* gt, int dtype, int B, int C, int H, int W,
+                                              const int32_t* edges, const int32_t* counts, int max_edges, int ks,
+                                              int kw, float sigma, float eps, int rows_mode, float w_l1, float w_kl,
+                                              float* grad_sr, double* terms, void* workspace, size_t workspace_bytes,
+                                              void* stream) {
+    SSLB_REQUIRE(sr && gt && edges && counts && terms && workspace, "null pointer");
+    SSLB_REQUIRE(rows_mode == SSL_B200_ROWS_EXP || rows_mode == SSL_B200_ROWS_NORM,
+                 "the loss is defined on exp / normalised rows");
+    SSLB_REQUIRE(workspace_bytes >= ssl_b200_loss_workspace_bytes(ks, max_edges), "workspace too small");
+    if (int e = check_sizes(ks, kw, H, W, C)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    SSLB_CUDA(cudaMemsetAsync(terms, 0, 3 * sizeof(double), st));
+    if (grad_sr) SSLB_CUDA(cudaMemsetAsync(grad_sr, 0, sizeof(float) * (size_t)B * C * H * W, st));
+    set_terms_count_kernel<<<1, 1, 0, st>>>(counts, terms);
+    if (int e = check_launch("set_terms_count")) return e;
+    if (max_edges <= 0) return 0;
+    const size_t rows_bytes = align256((size_t)max_edges * ks * ks * sizeof(float));
+    char* ws = static_cast<char*>(workspace);
+    float* rows_sr = reinterpret_cast<float*>(ws);
+    float* rows_gt = reinterpret_cast<float*>(ws + rows_bytes);
+    double* scratch = reinterpret_cast<double*>(ws + 2 * rows_bytes);
+    if (int e = ssl_b200_ssg_rows_forward(sr, gt, dtype, B, C, H, W, edges, counts, max_edges, ks, kw, sigma, eps,
+                                          rows_mode, rows_sr, rows_gt, stream)) return e;
+    // rows_sr is overwritten in place by dL/dq when a gradient is wanted
+    if (int e = ssl_b200_row_loss(rows_sr, rows_gt, counts, max_edges, ks, kw, C, sigma, rows_mode, w_l1, w_kl,
+                                  grad_sr ? rows_sr : nullptr, terms, scratch, stream)) return e;
+    if (grad_sr)
+        if (int e = ssl_b200_ssg_rows_backward(sr, dtype, B, C, H, W, edges, counts, max_edges, ks, kw, rows_sr,
+                                               grad_sr, stream)) return e;
+    return 0;
+}
+
+namespace {
+
+struct HostArena {
+    int dev = -1;
+    char* base = nullptr;
+    size_t bytes = 0;
+    int32_t* counts_pinned = nullptr;
+};
+
+HostArena& arena() {
+    static thread_local HostArena a;
+    return a;
+}
+
+int arena_reserve(size_t bytes) {
+    HostArena& a = arena();
+    int dev = 0;
+    SSLB_CUDA(cudaGetDevice(&dev));
+    if (a.dev == dev && a.bytes >= bytes) return 0;
+    if (a.base) {
+        SSLB_CUDA(cudaDeviceSynchronize());
+        SSLB_CUDA(cudaFree(a.base));
+        a.base = nullptr;
+        a.bytes = 0;
+    }
+    if (!a.counts_pinned) SSLB_CUDA(cudaMallocHost(&a.counts_pinned, 4 * sizeof(int32_t)));
+    SSLB_CUDA(cudaMalloc(&a.base, bytes));
+    a.bytes = bytes;
+    a.dev = dev;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int ssl_b200_release_host_arena(void) {
+    HostArena& a = arena();
+    if (a.base) {
+        SSLB_CUDA(cudaDeviceSynchronize());
+        SSLB_CUDA(cudaFree(a.base));
+    }
+    if (a.counts_pinned) SSLB_CUDA(cudaFreeHost(a.counts_pinned));
+    a = HostArena{};
+    return 0;
+}
+
+extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_host, const float* mask_host,
+                                       int mask_channels, int B, int C, int H, int W, int mask_stride, int ks, int kw,
+                                       float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* loss_host,
+                                       float* grad_host, int64_t* n_rows_host, void* stream) {
+    SSLB_REQUIRE(sr_host && gt_host && mask_host && loss_host, "null pointer");
+    SSLB_REQUIRE(B >= 1 && mask_channels >= 1, "bad shape");
+    if (int e = check_sizes(ks, kw, H, W, C)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_px = (size_t)B * H * W, img_bytes = align256(n_px * C * sizeof(float));
+    const size_t mask_bytes = align256(n_px * mask_channels * sizeof(float));
+    const size_t edges_bytes = align256(n_px * sizeof(int32_t)), counts_bytes = align256((2 + B) * sizeof(int32_t));
+    const size_t el_ws = align256(ssl_b200_edge_list_workspace_bytes((int64_t)n_px));
+    const size_t small_bytes = 256;  // terms double[3] | loss float[3] | inv_n float
+    const size_t fixed = 3 * img_bytes + mask_bytes + edges_bytes + counts_bytes + el_ws + small_bytes;
+    // first pass with the arena we have (or the fixed part); rows need the edge count
+    HostArena& a = arena();
+    if (int e = arena_reserve(fixed + ssl_b200_loss_workspace_bytes(ks, (int)(n_px / 8 + 1)))) return e;
+    auto carve = [&](char*& p, size_t b) { char* r = p; p += b; return r; };
+    char* p = a.base;
+    float* d_mask = (float*)carve(p, mask_bytes);
+    int32_t* d_edges = (int32_t*)carve(p, edges_bytes);
+    int32_t* d_counts = (int32_t*)carve(p, counts_bytes);
+    void* d_elws = carve(p, el_ws);
+    char* d_small = carve(p, small_bytes);
+    // mask first, so the edge count comes back while the images are still on the wire
+    SSLB_CUDA(cudaMemcpyAsync(d_mask, mask_host, n_px * mask_channels * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int e = ssl_b200_build_edge_list(d_mask, B, mask_channels, H, W, mask_stride, d_edges, (int)n_px, d_counts,
+                                         d_elws, el_ws, stream)) return e;
+    SSLB_CUDA(cudaMemcpyAsync(a.counts_pinned, d_counts, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    cudaEvent_t counted;
+    SSLB_CUDA(cudaEventCreateWithFlags(&counted, cudaEventDisableTiming));
+    SSLB_CUDA(cudaEventRecord(counted, st));
+    // images may land anywhere after the fixed head: if the arena must grow they are re-sent
+    auto place_images = [&](char* q, float*& d_sr, float*& d_gt, float*& d_grad, char*& d_ws) {
+        d_sr = (float*)carve(q, img_bytes);
+        d_gt = (float*)carve(q, img_bytes);
+        d_grad = (float*)carve(q, img_bytes);
+        d_ws = q;
+    };
+    float *d_sr, *d_gt, *d_grad;
+    char* d_ws;
+    place_images(p, d_sr, d_gt, d_grad, d_ws);
+    SSLB_CUDA(cudaMemcpyAsync(d_sr, sr_host, n_px * C * sizeof(float), cudaMemcpyHostToDevice, st));
+    SSLB_CUDA(cudaMemcpyAsync(d_gt, gt_host, n_px * C * sizeof(float), cudaMemcpyHostToDevice, st));
+    cudaError_t ce = cudaEventSynchronize(counted);
+    cudaEventDestroy(counted);
+    if (ce != cudaSuccess) return fail((int)ce, "edge count readback: %s", cudaGetErrorString(ce));
+    const int n_rows = a.counts_pinned[0];
+    const size_t ws_bytes = ssl_b200_loss_workspace_bytes(ks, n_rows);
+    if (fixed + ws_bytes > a.bytes) {
+        // grow (rare: first call, or a denser mask than ever seen) and redo the uploads
+        if (int e = arena_reserve(fixed + ws_bytes + ws_bytes / 4)) return e;
+        return ssl_b200_loss_step_host(sr_host, gt_host, mask_host, mask_channels, B, C, H, W, mask_stride, ks, kw,
+                                       sigma, eps, rows_mode, w_l1, w_kl, loss_host, grad_host, n_rows_host, stream);
+    }
+    double* d_terms = (double*)d_small;
+    float* d_loss = (float*)(d_small + 64);
+    float* d_inv_n = (float*)(d_small + 128);
+    if (int e = ssl_b200_loss_forward_backward(d_sr, d_gt, SSL_B200_F32, B, C, H, W, d_edges, d_counts, n_rows, ks, kw,
+                                               sigma, eps, rows_mode, w_l1, w_kl, grad_host ? d_grad : nullptr,
+                                               d_terms, d_ws, ws_bytes, stream)) return e;
+    finalize_loss_kernel<<<1, 1, 0, st>>>(d_terms, ks * ks, w_l1, w_kl, d_loss, d_inv_n);
+    if (int e = check_launch("finalize_loss")) return e;
+    SSLB_CUDA(cudaMemcpyAsync(loss_host, d_loss, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (grad_host) {
+        const long long n4 = (long long)(img_bytes / sizeof(float4));  // the pad is ours: scale whole float4s
+        DeviceInfo di;
+        if (int e = device_info(&di)) return e;
+        scale_kernel<<<di.sm_count * 8, 256, 0, st>>>((float4*)d_grad, n4, d_inv_n);
+        if (int e = check_launch("scale_grad")) return e;
+        SSLB_CUDA(cudaMemcpyAsync(grad_host, d_grad, n_px * C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    SSLB_CUDA(cudaStreamSynchronize(st));
+    if (n_rows_host) *n_rows_host = n_rows;
+    return 0;
+}
+
+extern "C" uint64_t ssl_b200_launch_count(void) { return launch_counter().load(std::memory_order_relaxed); }

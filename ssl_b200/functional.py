@@ -216,19 +216,15 @@ class _SSLLoss(torch.autograd.Function):
         dev = sr_c.device
         need_grad = ctx.needs_input_grad[0]
         c = sr_c.shape[1]
-        sums = torch.zeros(2, dtype=torch.float64, device=dev)
-        grad = None
-        if n:
-            rows_sr, rows_gt = _rows_forward(sr_c, gt_c, el, n, ks, kw, sigma, eps, mode)
-            scratch = torch.empty(2 * int(_lib.load().ssl_b200_row_loss_blocks()), dtype=torch.float64, device=dev)
-            with torch.cuda.device(dev):
-                _lib.call("ssl_b200_row_loss", _ptr(rows_sr), _ptr(rows_gt), _ptr(el.counts), n, ks, kw, c,
-                          float(sigma), mode, float(w_l1), float(w_kl), _ptr(rows_sr if need_grad else None),
-                          _ptr(sums), _ptr(scratch), _stream())
-            if need_grad:
-                grad = _rows_backward(sr_c, el, n, ks, kw, rows_sr)  # rows_sr now holds dL/dq (unnormalised)
-        n_rows = el.counts[0:1].to(torch.float64)
-        terms = torch.cat([sums, n_rows])
+        terms = torch.empty(3, dtype=torch.float64, device=dev)   # sum|d|, sum KL, n_rows
+        grad = torch.empty(sr_c.shape, dtype=torch.float32, device=dev) if need_grad else None
+        ws_bytes = int(_lib.load().ssl_b200_loss_workspace_bytes(ks, n))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        b, _, h, w = sr_c.shape
+        with torch.cuda.device(dev):
+            _lib.call("ssl_b200_loss_forward_backward", _ptr(sr_c), _ptr(gt_c), _lib.dtype_code(sr_c.dtype), b, c, h, w,
+                      _ptr(el.edges), _ptr(el.counts), n, ks, kw, float(sigma), float(eps), mode, float(w_l1),
+                      float(w_kl), _ptr(grad), _ptr(terms), _ptr(ws), ws_bytes, _stream())
         if reducer is not None:
             terms = reducer(terms)
         n_tot = (terms[2] * (ks * ks)).clamp_min(1.0)
@@ -250,3 +246,36 @@ class _SSLLoss(torch.autograd.Function):
             return (None,) * 12
         g = (ctx.grad_sr * (g_total.to(torch.float32) * ctx.inv_n)).to(ctx.sr_dtype)
         return (g,) + (None,) * 11
+
+
+def ssl_step_host(sr, gt, mask, kernel_size_search: int = 25, kernel_size_window: int = 9, sigma: float = 0.004,
+                  generalization: bool = True, eps: float = 1e-10, loss_weight: float = 1.0, kl_weight: float = 0.0,
+                  mask_stride: int = 0, want_grad: bool = True, out_grad: Optional[torch.Tensor] = None,
+                  device: Optional[torch.device] = None):
+    """The whole SSL block on HOST tensors through the C ABI's host entry (ssl_b200_loss_step_host):
+    H2D of sr/gt/mask, edge list, fused step, 'mean', D2H of (total, l1, kl) and d total/d sr.
+
+    sr, gt: fp32 CPU [B,C,H,W]; mask: fp32 CPU [B,1|3,H,W] (pin them for full copy speed).
+    Returns (loss[3] CPU tensor, grad CPU tensor or None, n_rows).  Synchronous.
+    """
+    for name, t in (("sr", sr), ("gt", gt), ("mask", mask)):
+        if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"ssl_step_host: `{name}` must be a contiguous fp32 CPU tensor")
+    if not torch.cuda.is_available():
+        raise RuntimeError("ssl_b200: no CUDA device; there is no CPU path")
+    b, c, h, w = sr.shape
+    if gt.shape != sr.shape or mask.shape[0] != b or tuple(mask.shape[-2:]) != (h, w):
+        raise ValueError("sr / gt / mask shapes do not agree")
+    _check_kernel_sizes(kernel_size_search, kernel_size_window, h, w)
+    loss = torch.empty(3, dtype=torch.float32).pin_memory()
+    grad = None
+    if want_grad:
+        grad = out_grad if out_grad is not None else torch.empty(sr.shape, dtype=torch.float32).pin_memory()
+    n_rows = ctypes.c_int64(0)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        _lib.call("ssl_b200_loss_step_host", _ptr(sr), _ptr(gt), _ptr(mask), mask.shape[1], b, c, h, w,
+                  int(mask_stride), int(kernel_size_search), int(kernel_size_window), float(sigma), float(eps),
+                  rows_mode(generalization), float(loss_weight), float(kl_weight), _ptr(loss), _ptr(grad),
+                  ctypes.byref(n_rows), _stream())
+    return loss, grad, int(n_rows.value)

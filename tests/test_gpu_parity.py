@@ -282,3 +282,30 @@ def test_config2_shape_properties_and_subsample_parity(dev):
         q = oracle.raw_distance(sr[b].numpy().astype(np.float64), pos[sel, 1:].astype(np.int32), 25, 9)
         want = oracle.rows_from_distance(q, 25, 9, 3, 0.004, True)
         _assert_rows(r[sel], want)
+
+
+def test_host_step_matches_device_path_and_oracle(dev):
+    """ssl_b200_loss_step_host (host buffers in, loss + gradient out) == ssl() on device tensors == oracle."""
+    import ssl_b200
+    from ssl_b200 import _lib, synth
+    sr, gt, mask = synth.make_case(3, 40, 44, seed=5, density=0.06)
+    mask[2] = 0
+    l1, kl, grad, n = oracle.loss_and_grad(sr.numpy().astype(np.float64), gt.numpy().astype(np.float64), mask.numpy(),
+                                           11, 5, 0.004, True, loss_weight=2.0, kl_weight=0.5)
+    before = _lib.load().ssl_b200_launch_count()
+    loss_h, grad_h, n_rows = ssl_b200.ssl_step_host(sr, gt, mask, 11, 5, 0.004, True, loss_weight=2.0, kl_weight=0.5)
+    assert _lib.load().ssl_b200_launch_count() - before >= 6   # edge list (3) + fwd + row loss (2) + bwd ...
+    assert n_rows == n
+    assert float(loss_h[1]) == pytest.approx(l1, rel=LOSS_RTOL)
+    assert float(loss_h[2]) == pytest.approx(kl, rel=2e-5)
+    assert float(loss_h[0]) == pytest.approx(l1 + kl, rel=LOSS_RTOL)
+    assert np.abs(grad_h.numpy() - grad).max() <= 2e-5 * np.abs(grad).max()
+    x = sr.to(dev).requires_grad_(True)
+    total = ssl_b200.ssl(x, gt.to(dev), mask.to(dev), 11, 5, 0.004, True, loss_weight=2.0, kl_weight=0.5)
+    total.backward()
+    assert float(total) == pytest.approx(float(loss_h[0]), rel=1e-6)
+    # the backward scatters with float atomics: equal up to summation order
+    assert np.abs(x.grad.cpu().numpy() - grad_h.numpy()).max() <= 1e-5 * np.abs(grad).max()
+    # empty batch through the host entry
+    loss0, grad0, n0 = ssl_b200.ssl_step_host(sr, gt, torch.zeros_like(mask), 11, 5)
+    assert n0 == 0 and float(loss0[0]) == 0.0 and float(grad0.abs().max()) == 0.0
