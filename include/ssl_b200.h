@@ -114,6 +114,20 @@ int ssl_b200_row_loss(const float* rows_sr, const float* rows_gt, const int32_t*
                       int ks, int kw, int C, float sigma, int rows_mode, float w_l1, float w_kl, float* gq,
                       double* sums, double* scratch, void* stream);
 
+/* ---- plane (tile-sharing) path -------------------------------------------------------------
+ * Same results as the entry points above, computed per image tile instead of per edge pixel: the
+ * squared-difference plane of every search offset is built once per tile and shared by all of its
+ * edge pixels (ssl_b200/csrc/plane_geom.cuh).  Available for C == 3 and the kernel sizes
+ * ssl_b200_plane_supported() accepts; the whole-step entry points pick it automatically. */
+int ssl_b200_plane_supported(int ks, int kw, int channel);
+
+/* Raw patch distances (ROWS_RAW, == ssl_b200_ssg_rows_forward(..., SSL_B200_ROWS_RAW, ...)) through
+ * the plane kernels.  workspace: ssl_b200_plane_rows_workspace_bytes() bytes of scratch. */
+size_t ssl_b200_plane_rows_workspace_bytes(int B, int H, int W, int ks, int kw, int max_edges);
+int ssl_b200_plane_rows_forward(const void* image, const void* image2, int dtype, int B, int C, int H, int W,
+                                const int32_t* edges, const int32_t* n_edges_dev, int max_edges, int ks, int kw,
+                                float* rows, float* rows2, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- whole step ------------------------------------------------------------------------- */
 
 /* The reference training-step block (realesrganssl_model.py:378-430: per-image loop, two

@@ -38,6 +38,11 @@ SIGNATURES = {
     "ssl_b200_row_loss_blocks": (_c_int, []),
     "ssl_b200_row_loss": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int,
                                    _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ssl_b200_plane_supported": (_c_int, [_c_int, _c_int, _c_int]),
+    "ssl_b200_plane_rows_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
+    "ssl_b200_plane_rows_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                             _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                                             _c_size_t, _c_void_p]),
     "ssl_b200_loss_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "ssl_b200_loss_forward_backward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                                 _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_float,

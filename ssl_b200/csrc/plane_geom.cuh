@@ -1,0 +1,220 @@
+// Geometry shared by the "plane" (tile-sharing) kernels: ssg_plane_fwd.cuh / ssg_plane_bwd.cuh.
+//
+// The point kernels (ssg_point.cuh) spend C*kw^2 (subtract, fma) pairs per (edge pixel, search
+// offset).  The plane kernels share that work between neighbouring edge pixels: for one search
+// offset d = (dy,dx) the squared-difference plane
+//     D_d(Y,X) = sum_c ( I(Y,X) - I(Y+dy,X+dx) )^2                      (reflect-padded coordinates)
+// is computed once per image tile, box-summed separably, and read by every edge pixel of the tile:
+//     q(p,d) = sum_{a in A(dy)} sum_{b in A(dx)} D_d(p + (a,b))  +  Eout(p,d)
+// with A(t) = [max(-K,-P-t), min(K,P-t)] the part of the window whose neighbour stays inside the
+// search area (the zero-padded unfold of loss_util.py:208-209 == the bounds test of
+// similarity.cu:43) and Eout the remaining terms, in which the neighbour counts as zero
+// (similarity.cu:46-47).  tests/dense_model.py is the NumPy statement of the same algebra.
+#pragma once
+
+#include "common.cuh"
+
+namespace sslb {
+
+// Compile-time geometry of one (k_search, k_window) configuration.
+template <int KS_, int KW_>
+struct PlaneCfg {
+    static constexpr int KS = KS_, KW = KW_;
+    static constexpr int P = KS / 2, K = KW / 2;
+    static constexpr int L = KS * KS;
+    static constexpr int G = 5;            // consecutive dx handled by one sweep thread
+    static constexpr int NWP = 5;          // warp pairs per CTA = consecutive dy per step
+    static constexpr int NPL = G * NWP;    // planes resident per step (<= 32: one lane each)
+    static constexpr int NDXG = (KS + G - 1) / G;
+    static constexpr int NDYS = (KS + NWP - 1) / NWP;
+    static constexpr int ROWS = 64;        // lanes of a warp pair = image rows of a tile incl. halo
+    static constexpr int THREADS = NWP * ROWS;
+    static constexpr int NCLS = 2 * K + 1; // clip classes per axis
+    // forward tiles (unpadded image coordinates of the edge pixels they own)
+    static constexpr int TYF = ROWS - 2 * K;
+    static constexpr int TXF = 64;
+    static constexpr int CH = 8;           // columns per sweep chunk
+    static constexpr int UNITS_X = TXF / CH;
+    static constexpr int SWEEP = TXF + CH;   // one chunk of halo: 2K <= CH columns
+    static constexpr int NCH = SWEEP / CH;
+    // shared image tile: row 0 <-> Y = Ytile0 - K - P, column ICOL0 <-> X = Xtile0 - K
+    static constexpr int IROWS = ROWS + 2 * P;
+    static constexpr int ICOL0 = ((P + 3) / 4) * 4;
+    static constexpr int ICOLS = ICOL0 + SWEEP + P + 4;
+    static constexpr int IPITCH = (((ICOLS + 3) / 4) | 1) * 4;  // 4 * odd: conflict-free float4 rows
+    // shared ring of box-summed planes
+    static constexpr int RING = 16;
+    static constexpr int SRP = RING + 1;                 // odd row pitch
+    static constexpr int SPS = (ROWS * SRP) | 1;         // odd plane stride
+    static_assert(KS % 2 == 1 && KW % 2 == 1 && KW <= KS && KW <= 9, "unsupported kernel sizes");
+    static_assert(NPL <= 32, "one lane per plane");
+    static_assert(2 * K <= CH, "gather lags the sweep by one chunk");
+};
+
+// in-area range of window offsets for search offset t, per axis
+__host__ __device__ constexpr int rng_lo(int t, int P, int K) { return -P - t > -K ? -P - t : -K; }
+__host__ __device__ constexpr int rng_hi(int t, int P, int K) { return P - t < K ? P - t : K; }
+// clip class of t: 0..K-1 clipped below (lo = -cls), K unclipped, K+1..2K clipped above (hi = 2K-cls)
+__host__ __device__ constexpr int clip_class(int t, int P, int K) {
+    return t < -(P - K) ? t + P : (t > P - K ? t - (P - K) + K : K);
+}
+__host__ __device__ constexpr int class_lo(int cls, int K) { return cls < K ? -cls : -K; }
+__host__ __device__ constexpr int class_hi(int cls, int K) { return cls > K ? 2 * K - cls : K; }
+
+// Edge pixels regrouped for the plane kernels.  A *unit* is an 8-column strip of a forward tile;
+// its edge pixels occupy consecutive *slots* (row-major inside the unit, count padded to a multiple
+// of 4 with empty slots) so that the 4 results a lane produces for one search offset are one
+// aligned float4 of the offset-major rows buffer  qT[offset][slot].
+struct PlaneLists {
+    int32_t* unit_start;   // [n_units + 1] first slot of each unit (exclusive scan of padded counts)
+    int32_t* slot_pix;     // [capacity] flat pixel index b*H*W + y*W + x, or -1 (padding)
+    int32_t* slot_rc;      // [capacity] (row lane << 8) | column in tile, or -1
+    int32_t* slot_map;     // [B*H*W] slot of each pixel, or -1
+    int32_t* counts;       // [4]: slots used, edges found, slots needed (uncapped), n_units
+};
+
+struct PlaneGeom {
+    int B, H, W;
+    int TYF, TXF, K;
+    int nty, ntx;          // forward tiles per image
+    int n_units;
+};
+
+inline PlaneGeom make_geom(int B, int H, int W, int TYF, int TXF, int K) {
+    PlaneGeom g;
+    g.B = B; g.H = H; g.W = W; g.TYF = TYF; g.TXF = TXF; g.K = K;
+    g.nty = (H + TYF - 1) / TYF;
+    g.ntx = (W + TXF - 1) / TXF;
+    g.n_units = B * g.nty * g.ntx * (TXF / 8);
+    return g;
+}
+
+struct PlaneListParams {
+    const float* mask;         // [B,mask_channels,H,W], or NULL: take the pixels of `edges`
+    int mask_channels, stride;
+    const int32_t* edges;      // flat pixel indices (ssl_b200_build_edge_list order)
+    const int32_t* n_edges_dev;
+    int max_edges;
+    PlaneGeom g;
+    int capacity;
+    int32_t* unit_count;   // [n_units] padded counts (scratch)
+    PlaneLists out;
+};
+
+__device__ __forceinline__ bool mask_is_edge(const float* mask, int mask_channels, int stride, int H, int W, int b,
+                                             int y, int x) {
+    const float v = __ldg(mask + ((long long)b * mask_channels * H + y) * W + x);
+    if (v != 1.0f) return false;  // exact compare, like the reference (loss_util.py:196)
+    return stride <= 1 || (y % stride) == (x % stride);
+}
+
+// The pixels of a flat edge list are marked -2 in slot_map before the unit passes run.
+__global__ void __launch_bounds__(256) plane_mark_edges_kernel(PlaneListParams p) {
+    const int mc = edge_count(p.n_edges_dev, p.max_edges);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc; i += gridDim.x * blockDim.x)
+        p.out.slot_map[p.edges[i]] = -2;
+}
+
+__device__ __forceinline__ bool unit_is_edge(const PlaneListParams& p, int b, int y, int x) {
+    if (p.mask) return mask_is_edge(p.mask, p.mask_channels, p.stride, p.g.H, p.g.W, b, y, x);
+    return p.out.slot_map[(b * p.g.H + y) * p.g.W + x] != -1;
+}
+
+// unit -> (b, ty, tx, cx)
+__device__ __forceinline__ void decode_unit(const PlaneGeom& g, int u, int& b, int& ty, int& tx, int& cx) {
+    const int ux = g.TXF / 8;
+    cx = u % ux; u /= ux;
+    tx = u % g.ntx; u /= g.ntx;
+    ty = u % g.nty;
+    b = u / g.nty;
+}
+
+// One warp per unit.  Pass 0 counts, pass 1 emits (after the scan).  The unit is walked row by row,
+// 8 columns x 4 rows per warp step, so ballot order == row-major order inside the unit.
+template <int PASS>
+__global__ void __launch_bounds__(256) plane_units_kernel(PlaneListParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.g.n_units) return;
+    int b, ty, tx, cx;
+    decode_unit(p.g, warp, b, ty, tx, cx);
+    const int y0 = ty * p.g.TYF, x0 = tx * p.g.TXF + cx * 8;
+    const int ly = lane >> 3, lx = lane & 7;
+    int running = PASS ? p.out.unit_start[warp] : 0;
+    const int base = running;
+    for (int yy = 0; yy < p.g.TYF; yy += 4) {
+        const int y = y0 + yy + ly, x = x0 + lx;
+        const bool e = (yy + ly) < p.g.TYF && y < p.g.H && x < p.g.W && unit_is_edge(p, b, y, x);
+        const unsigned ball = __ballot_sync(0xffffffffu, e);
+        if (PASS && e) {
+            const int slot = running + __popc(ball & ((1u << lane) - 1u));
+            if (slot < p.capacity) {
+                p.out.slot_pix[slot] = (b * p.g.H + y) * p.g.W + x;
+                p.out.slot_rc[slot] = ((yy + ly + p.g.K) << 8) | (cx * 8 + lx);
+                p.out.slot_map[(b * p.g.H + y) * p.g.W + x] = slot;
+            }
+        }
+        running += __popc(ball);
+    }
+    if (PASS == 0) {
+        if (lane == 0) {
+            p.unit_count[warp] = (running + 3) & ~3;
+            if (running) atomicAdd(p.out.counts + 1, running);
+        }
+    } else {
+        // padding slots of this unit
+        const int end = p.out.unit_start[warp + 1];
+        for (int s = running + lane; s < end; s += 32)
+            if (s < p.capacity) { p.out.slot_pix[s] = -1; p.out.slot_rc[s] = -1; }
+        (void)base;
+    }
+}
+
+// Single block: exclusive scan of the padded unit counts.
+__global__ void __launch_bounds__(1024) plane_units_scan_kernel(PlaneListParams p) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < p.g.n_units; start += 1024) {
+        const int i = start + threadIdx.x;
+        const int v = i < p.g.n_units ? p.unit_count[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (i < p.g.n_units) p.out.unit_start[i] = carry + (warp ? warp_tot[warp - 1] : 0) + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int total = carry_s;
+        p.out.unit_start[p.g.n_units] = total;
+        p.out.counts[0] = total < p.capacity ? total : p.capacity;
+        p.out.counts[2] = total;
+        p.out.counts[3] = p.g.n_units;
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_i32_kernel(int32_t* p, long long n, int32_t v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+}  // namespace sslb

@@ -1,0 +1,130 @@
+// Row loss on the offset-major rows of the plane path: qT[d][slot].
+//
+// One block owns 32 consecutive slots and keeps both of their rows (SR and GT, KS*KS entries each)
+// in shared memory, so the exp / normalise tail of loss_util.py:234-243, the L1 (basic_loss.py:
+// 14-16,59-66) and KL (basic_loss.py:269-282) numerators and the whole adjoint chain down to
+// dL/dq cost one read of each rows buffer and one write (dL/dq overwrites q_sr in place).
+// It also emits, per slot, the sum of dL/dq over every clip class: the weights of the
+// out-of-area terms (similarity.cu:123-124) used by the plane backward.
+#pragma once
+
+#include "plane_geom.cuh"
+#include "row_ops.cuh"
+
+namespace sslb {
+
+struct RowLossTParams {
+    float* qs;             // [L][cap] in: q of SR, out: dL/dq (when want_grad)
+    const float* qg;       // [L][cap] q of GT
+    const int32_t* slot_pix;
+    const int32_t* counts; // counts[0] = slots in use
+    int cap, L, KS, P, K;
+    float denom, sigma, eps, chain;
+    int mode, want_grad;
+    float w_l1, w_kl;
+    float* gcls;           // [cap][(2K+1)^2] or NULL
+    double* scratch;       // [2 * gridDim.x]
+};
+
+constexpr int kRowTThreads = 256;
+constexpr int kRowTPhases = kRowTThreads / 32;
+
+__global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams p) {
+    extern __shared__ float rl_smem[];
+    float* es = rl_smem;                // [L][32]
+    float* et = es + p.L * 32;          // [L][32]
+    __shared__ float red[2][kRowTPhases][32];
+    __shared__ double dred[32];
+    const int s = threadIdx.x & 31, ph = threadIdx.x >> 5;
+    const int n_slots = min(p.counts[0], p.cap);
+    double l1_tot = 0.0, kl_tot = 0.0;
+    for (int slot0 = blockIdx.x * 32; slot0 < n_slots; slot0 += gridDim.x * 32) {
+        const int slot = slot0 + s;
+        const bool valid = slot < n_slots && p.slot_pix[slot] >= 0;
+        // pass 1: e = exp(-1 * (q / (C kw^2)) / sigma), partial row sums
+        float zs = 0.f, zt = 0.f;
+        for (int d = ph; d < p.L; d += kRowTPhases) {
+            float a = 0.f, b = 0.f;
+            if (valid) {
+                a = expf(-1.0f * (p.qs[(long long)d * p.cap + slot] / p.denom) / p.sigma);
+                b = expf(-1.0f * (p.qg[(long long)d * p.cap + slot] / p.denom) / p.sigma);
+            }
+            es[d * 32 + s] = a;
+            et[d * 32 + s] = b;
+            zs += a;
+            zt += b;
+        }
+        red[0][ph][s] = zs;
+        red[1][ph][s] = zt;
+        __syncthreads();
+        float rs = 1.f, rt = 1.f;
+        if (p.mode == SSL_B200_ROWS_NORM) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int k = 0; k < kRowTPhases; ++k) { a += red[0][k][s]; b += red[1][k][s]; }
+            rs = 1.0f / (a + p.eps);
+            rt = 1.0f / (b + p.eps);
+        }
+        __syncthreads();
+        // pass 2: rows, loss terms, dL/drow; es <- s, et <- g
+        float l1 = 0.f, kl = 0.f, dot = 0.f;
+        for (int d = ph; d < p.L; d += kRowTPhases) {
+            const float sv = rs * es[d * 32 + s], tv = rt * et[d * 32 + s];
+            const float df = sv - tv;
+            l1 += fabsf(df);
+            float g = p.w_l1 * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+            if (p.w_kl != 0.f) {
+                const float sc = fmaxf(sv, 1e-10f), tc = fmaxf(tv, 1e-10f);
+                kl += kl_term(sc, tc) + (p.mode == SSL_B200_ROWS_NORM ? ((tc - tv) - (sc - sv)) : (tc - sc));
+                if (sv > 1e-10f) g -= p.w_kl * tc / sc;
+            }
+            if (!valid) g = 0.f;
+            dot = fmaf(g, sv, dot);
+            es[d * 32 + s] = sv;
+            et[d * 32 + s] = g;
+        }
+        if (valid) { l1_tot += (double)l1; kl_tot += (double)kl; }
+        if (p.want_grad) {
+            red[0][ph][s] = dot;
+            __syncthreads();
+            float dsum = 0.f;
+            if (p.mode == SSL_B200_ROWS_NORM) {
+#pragma unroll
+                for (int k = 0; k < kRowTPhases; ++k) dsum += red[0][k][s];
+            }
+            // pass 3: dL/dq = chain * s * (g - sum_m g_m s_m)   (EXP rows: chain * e * g)
+            for (int d = ph; d < p.L; d += kRowTPhases) {
+                const float gq = p.chain * es[d * 32 + s] * (et[d * 32 + s] - dsum);
+                es[d * 32 + s] = gq;
+                if (slot < n_slots) p.qs[(long long)d * p.cap + slot] = gq;
+            }
+            __syncthreads();
+            // pass 4: per clip class sums of dL/dq (classes with nothing out of area are skipped)
+            if (p.gcls && slot < n_slots) {
+                const int NC = 2 * p.K + 1, U = p.P - p.K;
+                for (int c = ph; c < NC * NC; c += kRowTPhases) {
+                    const int ca = c / NC, cb = c % NC;
+                    float acc = 0.f;
+                    if (ca != p.K || cb != p.K) {
+                        const int dy0 = ca < p.K ? ca - p.P : (ca > p.K ? U + (ca - p.K) : -U);
+                        const int dy1 = ca == p.K ? U : dy0;
+                        const int dx0 = cb < p.K ? cb - p.P : (cb > p.K ? U + (cb - p.K) : -U);
+                        const int dx1 = cb == p.K ? U : dx0;
+                        for (int dy = dy0; dy <= dy1; ++dy)
+                            for (int dx = dx0; dx <= dx1; ++dx) acc += es[((dy + p.P) * p.KS + dx + p.P) * 32 + s];
+                    }
+                    p.gcls[(long long)slot * (NC * NC) + c] = acc;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    l1_tot = block_sum(l1_tot, dred);
+    kl_tot = block_sum(kl_tot, dred);
+    if (threadIdx.x == 0) {
+        p.scratch[2 * blockIdx.x] = l1_tot;
+        p.scratch[2 * blockIdx.x + 1] = kl_tot;
+    }
+}
+
+}  // namespace sslb

@@ -1,0 +1,301 @@
+// Forward "plane" kernels: raw patch distances q(p,d) of every edge pixel of a batch, offset-major.
+//
+// One CTA owns one forward tile (TYF x TXF edge-pixel positions of one image) and one group of G
+// consecutive dx.  Its NWP warp pairs take NWP consecutive dy each step; a sweep thread is one
+// image row (lane) of one (dy, dx-group) and walks along X in chunks of 8 columns:
+//     D_j[i]   = sum_c ( I(Y, X+i) - I(Y+dy, X+i+dx0+j) )^2          8 x G values in registers
+//     S_j[i]   = sum of the last l(dx0+j) values of D_j               (pairwise tree, no subtraction)
+// and stores S into a 16-column shared ring, shifted so that every plane is read at column px+K.
+// After each chunk the CTA gathers the chunk's edge pixels: lane <-> plane, 4 slots per lane,
+//     q(p,d) = sum_{a in A(dy)} S_d[py+a][px+K] + Eout(p, class(dy), class(dx))
+// and writes one float4 of qT[d][slot..slot+3].
+//
+// Reference: GAN-Based-SR/basicsr/losses/similarity/similarity.cu:5-54 (same sums, regrouped);
+// the algebra is restated and checked against the oracle in tests/dense_model.py.
+#pragma once
+
+#include "plane_geom.cuh"
+
+namespace sslb {
+
+struct PlaneFwdParams {
+    const void* img[2];      // [B,3,H,W]; blockIdx.z selects
+    float* qT[2];            // [KS*KS][cap]
+    const float* eout[2];    // [cap][NCLS*NCLS]
+    PlaneLists lists;
+    PlaneGeom g;
+    int cap;
+};
+
+// ---- Eout tables -------------------------------------------------------------------------
+// eout[slot][ca*NCLS+cb] = sum over window offsets (a,b) outside A(ca) x A(cb) of sum_c I(p+(a,b))^2.
+// One warp per slot; all sums are over non-negative terms.
+template <typename T, typename Cfg>
+__global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
+    constexpr int K = Cfg::K, KW = Cfg::KW, NC = Cfg::NCLS, NW = KW * KW;
+    __shared__ float sE[4][NW], sRout[4][KW * NC], sRfull[4][KW];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_slots = min(p.lists.counts[0], p.cap);
+    const int H = p.g.H, W = p.g.W;
+    for (int slot = blockIdx.x * 4 + w; slot < n_slots; slot += gridDim.x * 4) {
+        const int pix = p.lists.slot_pix[slot];
+        float* out = const_cast<float*>(p.eout[blockIdx.y]) + (long long)slot * (NC * NC);
+        if (pix < 0) {
+            for (int i = lane; i < NC * NC; i += 32) out[i] = 0.f;
+            continue;
+        }
+        const int hw = H * W, b = pix / hw, rem = pix - b * hw, y = rem / W, x = rem - y * W;
+        const T* img = static_cast<const T*>(p.img[blockIdx.y]) + (long long)b * 3 * hw;
+        for (int i = lane; i < NW; i += 32) {
+            const int a = i / KW - K, bb = i % KW - K;
+            const int sy = reflect_idx(y + a, H), sx = reflect_idx(x + bb, W);
+            float e = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = load_as_float(img + (long long)c * hw + sy * W + sx);
+                e = fmaf(v, v, e);
+            }
+            sE[w][i] = e;
+        }
+        __syncwarp();
+        for (int i = lane; i < KW * NC; i += 32) {
+            const int a = i / NC, cb = i % NC;
+            const int lo = class_lo(cb, K), hi = class_hi(cb, K);
+            float s = 0.f;
+            for (int bb = -K; bb <= K; ++bb)
+                if (bb < lo || bb > hi) s += sE[w][a * KW + bb + K];
+            sRout[w][i] = s;
+        }
+        if (lane < KW) {
+            float s = 0.f;
+            for (int bb = 0; bb < KW; ++bb) s += sE[w][lane * KW + bb];
+            sRfull[w][lane] = s;
+        }
+        __syncwarp();
+        for (int i = lane; i < NC * NC; i += 32) {
+            const int ca = i / NC, cb = i % NC;
+            const int lo = class_lo(ca, K), hi = class_hi(ca, K);
+            float s = 0.f;
+            for (int a = -K; a <= K; ++a) s += (a < lo || a > hi) ? sRfull[w][a + K] : sRout[w][(a + K) * NC + cb];
+            out[i] = s;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- shared image tile -------------------------------------------------------------------
+// tile[c][row][col]: row 0 <-> padded Y = Ytile0 - K - P, col ICOL0 <-> padded X = Xtile0 - K;
+// reflect pad of loss_util.py:189-191 by index mapping, zero outside the padded image.
+template <typename T, typename Cfg>
+__device__ __forceinline__ void load_plane_tile(const T* img, float* tile, int H, int W, int Yrow0, int Xcol0) {
+    constexpr int P = Cfg::P;
+    const int Hp = H + 2 * P, Wp = W + 2 * P;
+    for (int idx = threadIdx.x; idx < 3 * Cfg::IROWS * Cfg::IPITCH; idx += blockDim.x) {
+        const int col = idx % Cfg::IPITCH, rr = idx / Cfg::IPITCH;
+        const int row = rr % Cfg::IROWS, c = rr / Cfg::IROWS;
+        const int Y = Yrow0 + row, X = Xcol0 + col;
+        float v = 0.f;
+        if (Y >= 0 && Y < Hp && X >= 0 && X < Wp)
+            v = load_as_float(img + ((long long)c * H + reflect_idx(Y - P, H)) * W + reflect_idx(X - P, W));
+        tile[idx] = v;
+    }
+}
+
+// Sum of the last LEN entries of w ending at index i (static indices; pairwise partial sums are
+// shared between the 8 outputs of a chunk by the caller through s2/s4/s8).
+template <int LEN>
+__device__ __forceinline__ float sum_last(const float* w, const float* s2, const float* s4, const float* s8, int i) {
+    if (LEN == 1) return w[i];
+    if (LEN == 2) return s2[i];
+    if (LEN == 3) return s2[i] + w[i - 2];
+    if (LEN == 4) return s4[i];
+    if (LEN == 5) return s4[i] + w[i - 4];
+    if (LEN == 6) return s4[i] + s2[i - 4];
+    if (LEN == 7) return s4[i] + (s2[i - 4] + w[i - 6]);
+    if (LEN == 8) return s8[i];
+    return s8[i - 1] + w[i];  // LEN == 9
+}
+
+template <typename Cfg, int GI>
+struct GroupConsts {
+    static constexpr int DX0 = -Cfg::P + GI * Cfg::G;
+    static constexpr int GJ = (Cfg::KS - GI * Cfg::G) < Cfg::G ? (Cfg::KS - GI * Cfg::G) : Cfg::G;
+    static constexpr int OFF = ((DX0 % 4) + 4) % 4;
+    static constexpr int NV4 = (OFF + 8 + GJ - 1 + 3) / 4;
+};
+
+// One chunk of one sweep thread: D, box sums, ring store.  wprev carries the previous chunk's D.
+template <typename Cfg, int GI>
+__device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splanes, int r, int dy, int wp, int k,
+                                                float (&wprev)[GroupConsts<Cfg, GI>::GJ][8]) {
+    using GC = GroupConsts<Cfg, GI>;
+    constexpr int P = Cfg::P, K = Cfg::K, GJ = GC::GJ, OFF = GC::OFF, NV4 = GC::NV4;
+    float d[GJ][8];
+#pragma unroll
+    for (int j = 0; j < GJ; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[j][i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* rowb = tile + (c * Cfg::IROWS + r + P) * Cfg::IPITCH + Cfg::ICOL0 + 8 * k;
+        const float* rown = tile + (c * Cfg::IROWS + r + P + dy) * Cfg::IPITCH + Cfg::ICOL0 + 8 * k + (GC::DX0 - OFF);
+        float base[8], nb[4 * NV4];
+        *reinterpret_cast<float4*>(&base[0]) = *reinterpret_cast<const float4*>(rowb);
+        *reinterpret_cast<float4*>(&base[4]) = *reinterpret_cast<const float4*>(rowb + 4);
+#pragma unroll
+        for (int v = 0; v < NV4; ++v)
+            *reinterpret_cast<float4*>(&nb[4 * v]) = *reinterpret_cast<const float4*>(rown + 4 * v);
+#pragma unroll
+        for (int j = 0; j < GJ; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float t = base[i] - nb[OFF + i + j];
+                d[j][i] = fmaf(t, t, d[j][i]);
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int dx = GC::DX0 + j;
+        const int bhi = rng_hi(dx, P, K), len = bhi - rng_lo(dx, P, K) + 1;
+        float w[16], s2[16], s4[16], s8[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { w[i] = wprev[j][i]; w[8 + i] = d[j][i]; wprev[j][i] = d[j][i]; }
+#pragma unroll
+        for (int i = 1; i < 16; ++i) s2[i] = w[i] + w[i - 1];
+#pragma unroll
+        for (int i = 3; i < 16; ++i) s4[i] = s2[i] + s2[i - 2];
+#pragma unroll
+        for (int i = 7; i < 16; ++i) s8[i] = s4[i] + s4[i - 4];
+        s2[0] = s4[0] = s4[1] = s4[2] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) s8[i] = 0.f;
+        float* sp = splanes + (wp * Cfg::G + j) * Cfg::SPS + r * Cfg::SRP;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float s;
+            switch (len) {  // len is a compile-time constant after unrolling over j
+                case 1: s = sum_last<1>(w, s2, s4, s8, 8 + i); break;
+                case 2: s = sum_last<2>(w, s2, s4, s8, 8 + i); break;
+                case 3: s = sum_last<3>(w, s2, s4, s8, 8 + i); break;
+                case 4: s = sum_last<4>(w, s2, s4, s8, 8 + i); break;
+                case 5: s = sum_last<5>(w, s2, s4, s8, 8 + i); break;
+                case 6: s = sum_last<6>(w, s2, s4, s8, 8 + i); break;
+                case 7: s = sum_last<7>(w, s2, s4, s8, 8 + i); break;
+                case 8: s = sum_last<8>(w, s2, s4, s8, 8 + i); break;
+                default: s = sum_last<9>(w, s2, s4, s8, 8 + i); break;
+            }
+            sp[(8 * k + i - bhi + K) & (Cfg::RING - 1)] = s;
+        }
+    }
+}
+
+template <typename Cfg, int GI>
+__device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const float* tile, float* splanes, int unit0,
+                                              int which) {
+    using GC = GroupConsts<Cfg, GI>;
+    constexpr int P = Cfg::P, K = Cfg::K, G = Cfg::G, GJ = GC::GJ, NC = Cfg::NCLS;
+    constexpr int NWARPS = Cfg::THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wp = tid / Cfg::ROWS, r = tid % Cfg::ROWS;
+    float* qT = p.qT[which];
+    const float* eout = p.eout[which];
+    const int cap = p.cap;
+    for (int dys = 0; dys < Cfg::NDYS; ++dys) {
+        const int dy = dys * Cfg::NWP + wp - P;
+        const bool dy_ok = dy <= P;
+        // gather-side constants of this lane's plane
+        const int pl_wp = lane / G, pl_j = lane % G;
+        const int g_dy = dys * Cfg::NWP + pl_wp - P, g_dx = GC::DX0 + pl_j;
+        const bool pl_ok = lane < Cfg::NPL && g_dy <= P && pl_j < GJ;
+        const int alo = rng_lo(g_dy, P, K), ahi = rng_hi(g_dy, P, K);
+        const int ca = clip_class(g_dy, P, K), cb = clip_class(g_dx, P, K);
+        const bool clipped = ca != K || cb != K;
+        const int cls = ca * NC + cb;
+        const long long qrow = (long long)((g_dy + P) * Cfg::KS + g_dx + P) * cap;
+        const float* myplane = splanes + lane * Cfg::SPS;
+
+        float wprev[GJ][8];
+#pragma unroll
+        for (int j = 0; j < GJ; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
+
+        for (int k = 0; k < Cfg::NCH; ++k) {
+            if (dy_ok) sweep_chunk_fwd<Cfg, GI>(tile, splanes, r, dy, wp, k, wprev);
+            __syncthreads();
+            if (k >= 1) {
+                const int u = unit0 + k - 1;
+                const int s0 = p.lists.unit_start[u];
+                const int s1 = min(p.lists.unit_start[u + 1], cap);
+                for (int gs = s0 + 4 * warp; gs < s1; gs += 4 * NWARPS) {
+                    const int4 rc4 = *reinterpret_cast<const int4*>(p.lists.slot_rc + gs);
+                    if (!pl_ok) continue;
+                    const int rcs[4] = {rc4.x, rc4.y, rc4.z, rc4.w};
+                    float out[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int rc = rcs[e];
+                        float acc = 0.f;
+                        if (rc >= 0) {
+                            const int re = rc >> 8, ex = rc & 255;
+                            const float* sp = myplane + re * Cfg::SRP + ((ex + 2 * K) & (Cfg::RING - 1));
+#pragma unroll
+                            for (int a = -K; a <= K; ++a)
+                                if (a >= alo && a <= ahi) acc += sp[a * Cfg::SRP];
+                            if (clipped) acc += __ldg(eout + (long long)(gs + e) * (NC * NC) + cls);
+                        }
+                        out[e] = acc;
+                    }
+                    *reinterpret_cast<float4*>(qT + qrow + gs) = make_float4(out[0], out[1], out[2], out[3]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <typename T, typename Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(PlaneFwdParams p) {
+    extern __shared__ float4 plane_smem4[];
+    float* tile = reinterpret_cast<float*>(plane_smem4);
+    float* splanes = tile + 3 * Cfg::IROWS * Cfg::IPITCH;
+    const int t = blockIdx.x;
+    const int tx = t % p.g.ntx, ty = (t / p.g.ntx) % p.g.nty, b = t / (p.g.ntx * p.g.nty);
+    const int unit0 = t * Cfg::UNITS_X;
+    if (p.lists.unit_start[unit0] >= min(p.lists.unit_start[unit0 + Cfg::UNITS_X], p.cap)) return;  // no edge pixel here
+    const int which = blockIdx.z;
+    const T* img = static_cast<const T*>(p.img[which]) + (long long)b * 3 * p.g.H * p.g.W;
+    // padded coordinates of the tile's first edge-pixel position: (P + ty*TYF, P + tx*TXF)
+    load_plane_tile<T, Cfg>(img, tile, p.g.H, p.g.W, Cfg::P + ty * Cfg::TYF - Cfg::K - Cfg::P,
+                            Cfg::P + tx * Cfg::TXF - Cfg::K - Cfg::ICOL0);
+    __syncthreads();
+    switch (blockIdx.y) {
+        case 0: run_group_fwd<Cfg, 0>(p, tile, splanes, unit0, which); break;
+        case 1: if constexpr (Cfg::NDXG > 1) run_group_fwd<Cfg, 1>(p, tile, splanes, unit0, which); break;
+        case 2: if constexpr (Cfg::NDXG > 2) run_group_fwd<Cfg, 2>(p, tile, splanes, unit0, which); break;
+        case 3: if constexpr (Cfg::NDXG > 3) run_group_fwd<Cfg, 3>(p, tile, splanes, unit0, which); break;
+        case 4: if constexpr (Cfg::NDXG > 4) run_group_fwd<Cfg, 4>(p, tile, splanes, unit0, which); break;
+        default: break;
+    }
+}
+
+template <typename Cfg>
+constexpr size_t plane_fwd_smem_bytes() {
+    return (size_t)(3 * Cfg::IROWS * Cfg::IPITCH + Cfg::NPL * Cfg::SPS) * sizeof(float);
+}
+
+// qT[d][slot] -> rows[i][d] in the reference's row order (i = position in the flat edge list).
+__global__ void __launch_bounds__(256) plane_rows_to_reference_kernel(const float* qT, int cap, const int32_t* edges,
+                                                                      const int32_t* n_edges_dev, int max_edges,
+                                                                      const int32_t* slot_map, int L, float* rows) {
+    const int mc = edge_count(n_edges_dev, max_edges);
+    for (int n = blockIdx.x; n < mc; n += gridDim.x) {
+        const int slot = slot_map[edges[n]];
+        for (int d = threadIdx.x; d < L; d += blockDim.x)
+            rows[(long long)n * L + d] = slot >= 0 && slot < cap ? qT[(long long)d * cap + slot] : 0.f;
+    }
+}
+
+}  // namespace sslb

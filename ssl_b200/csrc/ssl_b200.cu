@@ -6,6 +6,7 @@
 #include "edge_list.cuh"
 #include "row_ops.cuh"
 #include "ssg_point.cuh"
+#include "plane_host.cuh"
 
 using namespace sslb;
 
@@ -240,11 +241,77 @@ extern "C" int ssl_b200_laplacian_mask(const void* gt, int dtype, int B, int H, 
     return check_launch("laplacian_mask");
 }
 
-// ---- whole step ---------------------------------------------------------------------------
+// ---- plane (tile-sharing) path ------------------------------------------------------------
+
+extern "C" int ssl_b200_plane_supported(int ks, int kw, int channel) { return plane_supported(ks, kw, channel) ? 1 : 0; }
 
 namespace {
 
-size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+// Workspace of a plane forward: lists | qT | qT2 | eout | eout2
+struct PlaneFwdLayout {
+    PlaneGeom g;
+    int cap;
+    PlaneListsLayout lists;
+    size_t off_q[2], off_eout[2], total;
+};
+
+template <typename Cfg>
+PlaneFwdLayout plane_fwd_layout(int B, int H, int W, int max_edges) {
+    PlaneFwdLayout l;
+    l.g = geom_for<Cfg>(B, H, W);
+    l.cap = slot_capacity(max_edges, l.g.n_units);
+    l.lists = plane_lists_layout(l.g, l.cap);
+    size_t o = l.lists.total;
+    for (int i = 0; i < 2; ++i) { l.off_q[i] = o; o += align256((size_t)Cfg::L * l.cap * sizeof(float)); }
+    for (int i = 0; i < 2; ++i) { l.off_eout[i] = o; o += align256((size_t)l.cap * Cfg::NCLS * Cfg::NCLS * sizeof(float)); }
+    l.total = o;
+    return l;
+}
+
+}  // namespace
+
+extern "C" size_t ssl_b200_plane_rows_workspace_bytes(int B, int H, int W, int ks, int kw, int max_edges) {
+    if (!plane_supported(ks, kw, 3) || B < 1 || H < 1 || W < 1 || max_edges < 0) return 0;
+    SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, { return plane_fwd_layout<Cfg>(B, H, W, max_edges).total; });
+}
+
+extern "C" int ssl_b200_plane_rows_forward(const void* image, const void* image2, int dtype, int B, int C, int H,
+                                           int W, const int32_t* edges, const int32_t* n_edges_dev, int max_edges,
+                                           int ks, int kw, float* rows, float* rows2, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+    SSLB_REQUIRE(image && rows && edges && workspace, "null pointer");
+    SSLB_REQUIRE((image2 == nullptr) == (rows2 == nullptr), "image2 and rows2 go together");
+    SSLB_REQUIRE(plane_supported(ks, kw, C), "no plane kernels for k_s=%d k_w=%d C=%d", ks, kw, C);
+    if (int e = check_sizes(ks, kw, H, W, C)) return e;
+    if (max_edges <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, {
+        const PlaneFwdLayout l = plane_fwd_layout<Cfg>(B, H, W, max_edges);
+        SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
+        char* ws = static_cast<char*>(workspace);
+        if (int e = launch_plane_lists(nullptr, 1, 0, edges, n_edges_dev, max_edges, l.g, l.cap, ws, st)) return e;
+        const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
+        float* q0 = reinterpret_cast<float*>(ws + l.off_q[0]);
+        float* q1 = image2 ? reinterpret_cast<float*>(ws + l.off_q[1]) : nullptr;
+        if (int e = launch_plane_forward_cfg<Cfg>(image, image2, dtype, l.g, lists, l.cap, q0, q1,
+                                                  reinterpret_cast<float*>(ws + l.off_eout[0]),
+                                                  image2 ? reinterpret_cast<float*>(ws + l.off_eout[1]) : nullptr, st))
+            return e;
+        DeviceInfo di;
+        if (int e = device_info(&di)) return e;
+        const int blocks = min(max_edges, di.sm_count * 16);
+        plane_rows_to_reference_kernel<<<blocks, 256, 0, st>>>(q0, l.cap, edges, n_edges_dev, max_edges, lists.slot_map,
+                                                               Cfg::L, rows);
+        if (image2)
+            plane_rows_to_reference_kernel<<<blocks, 256, 0, st>>>(q1, l.cap, edges, n_edges_dev, max_edges,
+                                                                   lists.slot_map, Cfg::L, rows2);
+        return check_launch("plane_rows_to_reference", image2 ? 2 : 1);
+    });
+}
+
+// ---- whole step ---------------------------------------------------------------------------
+
+namespace {
 
 // [terms: sum|d|, sumKL, n_rows] -> loss[0..2] = total, w_l1*L1, w_kl*KL and inv_n = 1/(n_rows*L)
 __global__ void finalize_loss_kernel(const double* terms, int L, float w_l1, float w_kl, float* loss, float* inv_n) {
