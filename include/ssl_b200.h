@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SSL_B200_ABI_VERSION 1
+#define SSL_B200_ABI_VERSION 2
 
 /* element types of image tensors */
 #define SSL_B200_F32 0
@@ -43,6 +43,11 @@ extern "C" {
 #define SSL_B200_ROWS_RAW 0  /* q: raw squared patch distance (similarity.cu output)          */
 #define SSL_B200_ROWS_EXP 1  /* e = exp(-q/(C*kw^2)/sigma)      (generalization=False)        */
 #define SSL_B200_ROWS_NORM 2 /* s = e / (sum e + eps)           (generalization=True)         */
+
+/* which kernels the whole-step entry points use */
+#define SSL_B200_PATH_AUTO 0   /* plane kernels when available and the mask is dense enough */
+#define SSL_B200_PATH_POINT 1  /* one CTA per edge pixel (ssg_point.cuh) */
+#define SSL_B200_PATH_PLANE 2  /* per-tile displacement planes (ssg_plane_*.cuh) */
 
 /* error codes beyond cudaError_t */
 #define SSL_B200_EINVAL 10001
@@ -138,12 +143,13 @@ int ssl_b200_plane_rows_forward(const void* image, const void* image2, int dtype
  *                the gradient before the 1/N of the 'mean' reduction (N = n_rows*ks*ks is only
  *                known once the counts of all ranks are: the caller scales)
  *   terms        double [3], OVERWRITTEN: sum|S_sr - S_gt|, sum KL, n_rows
- *   workspace    ssl_b200_loss_workspace_bytes(ks, max_edges) bytes of scratch (rows never leave it) */
-size_t ssl_b200_loss_workspace_bytes(int ks, int max_edges);
+ *   workspace    ssl_b200_loss_workspace_bytes(...) bytes of scratch (rows never leave it)
+ *   path         SSL_B200_PATH_*; the same value must be given to ssl_b200_loss_workspace_bytes */
+size_t ssl_b200_loss_workspace_bytes(int B, int C, int H, int W, int ks, int kw, int max_edges, int path);
 int ssl_b200_loss_forward_backward(const void* sr, const void* gt, int dtype, int B, int C, int H, int W,
                                    const int32_t* edges, const int32_t* counts, int max_edges, int ks, int kw,
                                    float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* grad_sr,
-                                   double* terms, void* workspace, size_t workspace_bytes, void* stream);
+                                   double* terms, void* workspace, size_t workspace_bytes, int path, void* stream);
 
 /* Same step on HOST buffers (the end-to-end call of a host-side plugin): copies sr/gt/mask to the
  * device, builds the edge list, runs the step, applies the 'mean' (single device: N is local) and

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libssl_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 ROWS_RAW, ROWS_EXP, ROWS_NORM = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
+PATH_AUTO, PATH_POINT, PATH_PLANE = 0, 1, 2
 
 _c_int, _c_float, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
@@ -43,11 +44,11 @@ SIGNATURES = {
     "ssl_b200_plane_rows_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                              _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                                              _c_size_t, _c_void_p]),
-    "ssl_b200_loss_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+    "ssl_b200_loss_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
     "ssl_b200_loss_forward_backward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                                 _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_float,
                                                 _c_int, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p,
-                                                _c_size_t, _c_void_p]),
+                                                _c_size_t, _c_int, _c_void_p]),
     "ssl_b200_loss_step_host": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                          _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_float, _c_float,
                                          _c_void_p, _c_void_p, _c_void_p, _c_void_p]),

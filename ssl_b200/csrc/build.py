@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libssl_b200.so")
 SOURCES = ["ssl_b200.cu"]
-HEADERS = ["common.cuh", "edge_list.cuh", "row_ops.cuh", "ssg_point.cuh", 
+HEADERS = ["common.cuh", "edge_list.cuh", "row_ops.cuh", "ssg_point.cuh", "plane_geom.cuh", "plane_host.cuh",
+           "ssg_plane_fwd.cuh", "ssg_plane_bwd.cuh", "row_loss_t.cuh",
            os.path.join(ROOT, "include", "ssl_b200.h")]
 
 

@@ -4,6 +4,7 @@
 #include "plane_geom.cuh"
 #include "row_loss_t.cuh"
 #include "ssg_plane_fwd.cuh"
+#include "ssg_plane_bwd.cuh"
 
 namespace sslb {
 
@@ -106,6 +107,109 @@ inline int launch_plane_forward_cfg(const void* img, const void* img2, int dtype
         k<<<dim3(tiles, Cfg::NDXG, n_img), Cfg::THREADS, smem, st>>>(p);
     });
     return check_launch("plane_forward", 2);
+}
+
+// ---- whole plane step ---------------------------------------------------------------------
+// Workspace: lists | qT[SR] (becomes dL/dq) | qT[GT] | eout[2] | gcls | wtab | scratch | bwd lists | gpart
+struct PlaneStepLayout {
+    PlaneGeom g;
+    int cap;
+    PlaneListsLayout lists;
+    size_t off_q[2], off_eout[2], off_gcls, off_wtab, off_scratch, off_tcols, off_tent, off_gpart, total;
+    int ntyb, ntxb, HT, WT, n_btiles, loss_blocks;
+};
+
+template <typename Cfg>
+inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int loss_blocks, bool want_grad) {
+    using BC = PlaneBwdCfg<Cfg>;
+    PlaneStepLayout l;
+    l.g = geom_for<Cfg>(B, H, W);
+    l.cap = slot_capacity(max_edges, l.g.n_units);
+    l.lists = plane_lists_layout(l.g, l.cap);
+    l.loss_blocks = loss_blocks;
+    const int Hp = H + 2 * Cfg::P, Wp = W + 2 * Cfg::P;
+    l.ntyb = (Hp + Cfg::ROWS - 1) / Cfg::ROWS;
+    l.ntxb = (Wp + BC::TXB - 1) / BC::TXB;
+    l.HT = l.ntyb * Cfg::ROWS;
+    l.WT = l.ntxb * BC::TXB;
+    l.n_btiles = B * l.ntyb * l.ntxb;
+    const size_t nc2 = (size_t)Cfg::NCLS * Cfg::NCLS;
+    size_t o = l.lists.total;
+    for (int i = 0; i < 2; ++i) { l.off_q[i] = o; o += align256((size_t)Cfg::L * l.cap * sizeof(float)); }
+    for (int i = 0; i < 2; ++i) { l.off_eout[i] = o; o += align256((size_t)l.cap * nc2 * sizeof(float)); }
+    l.off_gcls = o; o += align256((size_t)l.cap * nc2 * sizeof(float));
+    l.off_wtab = o; o += align256((size_t)l.cap * Cfg::KW * Cfg::KW * sizeof(float));
+    l.off_scratch = o; o += align256((size_t)2 * loss_blocks * sizeof(double));
+    l.off_tcols = o; l.off_tent = o; l.off_gpart = o;
+    if (want_grad) {
+        o += align256((size_t)l.n_btiles * (BC::RCOLS + 1) * sizeof(int32_t));
+        l.off_tent = o; o += align256((size_t)l.n_btiles * BC::LIST_STRIDE * sizeof(int32_t));
+        l.off_gpart = o; o += align256((size_t)Cfg::NDXG * B * 3 * l.HT * l.WT * sizeof(float));
+    }
+    l.total = o;
+    return l;
+}
+
+template <typename Cfg>
+inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int B, int H, int W, const int32_t* edges,
+                                 const int32_t* counts, int max_edges, float sigma, float eps, int rows_mode,
+                                 float w_l1, float w_kl, float* grad_sr, double* terms, void* workspace,
+                                 size_t workspace_bytes, cudaStream_t st) {
+    using BC = PlaneBwdCfg<Cfg>;
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const int loss_blocks = di.sm_count;
+    const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, loss_blocks, grad_sr != nullptr);
+    SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
+    char* ws = static_cast<char*>(workspace);
+    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st)) return e;
+    const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
+    float* q_sr = reinterpret_cast<float*>(ws + l.off_q[0]);
+    float* q_gt = reinterpret_cast<float*>(ws + l.off_q[1]);
+    if (int e = launch_plane_forward_cfg<Cfg>(sr, gt, dtype, l.g, lists, l.cap, q_sr, q_gt,
+                                              reinterpret_cast<float*>(ws + l.off_eout[0]),
+                                              reinterpret_cast<float*>(ws + l.off_eout[1]), st)) return e;
+    // rows -> loss terms and dL/dq (in place over q_sr) + per-class sums
+    RowLossTParams rp{};
+    rp.qs = q_sr; rp.qg = q_gt; rp.slot_pix = lists.slot_pix; rp.counts = lists.counts;
+    rp.cap = l.cap; rp.L = Cfg::L; rp.KS = Cfg::KS; rp.P = Cfg::P; rp.K = Cfg::K;
+    rp.denom = 3.f * (float)(Cfg::KW * Cfg::KW); rp.sigma = sigma; rp.eps = eps;
+    rp.chain = -1.0f / (sigma * 3.f * (float)(Cfg::KW * Cfg::KW));
+    rp.mode = rows_mode; rp.want_grad = grad_sr ? 1 : 0; rp.w_l1 = w_l1; rp.w_kl = w_kl;
+    rp.gcls = grad_sr ? reinterpret_cast<float*>(ws + l.off_gcls) : nullptr;
+    rp.scratch = reinterpret_cast<double*>(ws + l.off_scratch);
+    const size_t rl_smem = (size_t)2 * Cfg::L * 32 * sizeof(float);
+    SSLB_CUDA(cudaFuncSetAttribute(row_loss_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl_smem));
+    row_loss_t_kernel<<<loss_blocks, kRowTThreads, rl_smem, st>>>(rp);
+    row_loss_finalize_kernel<<<1, 32, 0, st>>>(rp.scratch, loss_blocks, terms);
+    if (int e = check_launch("row_loss_t", 2)) return e;
+    if (!grad_sr) return 0;
+    PlaneBwdParams bp{};
+    bp.img = sr; bp.gqT = q_sr;
+    int32_t* tcols = reinterpret_cast<int32_t*>(ws + l.off_tcols);
+    int32_t* tent = reinterpret_cast<int32_t*>(ws + l.off_tent);
+    bp.tile_cols = tcols; bp.tile_ent = tent;
+    bp.gpart = reinterpret_cast<float*>(ws + l.off_gpart);
+    bp.slot_map = lists.slot_map;
+    bp.B = B; bp.H = H; bp.W = W; bp.cap = l.cap;
+    bp.ntyb = l.ntyb; bp.ntxb = l.ntxb; bp.HT = l.HT; bp.WT = l.WT;
+    plane_bwd_lists_kernel<Cfg><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tent);
+    const size_t smem = plane_bwd_smem_bytes<Cfg>();
+    SSLB_REQUIRE(smem <= (size_t)di.max_smem_optin, "plane backward needs %zu B of shared memory", smem);
+    PlaneFinishParams fp{};
+    fp.img = sr; fp.gpart = bp.gpart; fp.wtab = reinterpret_cast<float*>(ws + l.off_wtab);
+    fp.slot_map = lists.slot_map; fp.grad = grad_sr;
+    fp.B = B; fp.H = H; fp.W = W; fp.HT = l.HT; fp.WT = l.WT; fp.n_parts = Cfg::NDXG; fp.cap = l.cap;
+    plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(rp.gcls, lists.counts, l.cap,
+                                                           reinterpret_cast<float*>(ws + l.off_wtab));
+    const long long npx = (long long)B * H * W;
+    SSLB_DISPATCH_DTYPE(dtype, T, {
+        auto k = ssg_plane_bwd_kernel<T, Cfg>;
+        SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<dim3(l.n_btiles, Cfg::NDXG), Cfg::THREADS, smem, st>>>(bp);
+        plane_finish_kernel<T, Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
+    });
+    return check_launch("plane_backward", 4);
 }
 
 }  // namespace sslb

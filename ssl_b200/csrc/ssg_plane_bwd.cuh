@@ -1,0 +1,412 @@
+// Backward "plane" kernels: dL/dimage from dL/dq held offset-major (gqT[d][slot]).
+//
+// Adjoint of ssg_plane_fwd.cuh, in gather form (no global atomics, fixed summation order).  For a
+// search offset d the contributions of all edge pixels are first spread into a sparse plane
+//     u_d = (gq(p,d) placed at p)  +  (gq(p,-d) placed at p-d)
+// (v-direction applied while placing, h-direction by the same "sum of the last l" tree as the
+// forward), which gives, for every pixel x of a tile,
+//     Gs_d(x) = sum_{p: x in p+A(dy)xA(dx)} gq(p,d) + sum_{p: x+d in p+A(-dy)xA(-dx)} gq(p,-d)
+// so that  dL/dIpad(x,c) = 2 sum_d ( I(x,c) - I(x+d,c) ) Gs_d(x)  + out-of-area terms
+// (similarity.cu:73-131: +v into the centre pixel, -v into the neighbour pixel; the second sum is
+// the neighbour role of x, re-indexed so that it is gathered at x too).  tests/dense_model.py holds
+// the NumPy statement of these placement rules.
+//
+// One CTA = one 64 x TXB tile of the PADDED image and one dx-group; its NWP workers (warp pairs,
+// lane = image row) take dy = w, w+NWP, ...  Workers run the same (dy, chunk) sequence skewed by one
+// phase each, so that at any time they add into different 8-column chunks of the shared
+// accumulator tile; a CTA barrier ends each phase (deterministic order, no atomics).
+#pragma once
+
+#include "plane_geom.cuh"
+#include "ssg_plane_fwd.cuh"
+
+namespace sslb {
+
+template <typename Cfg>
+struct PlaneBwdCfg {
+    static constexpr int P = Cfg::P, K = Cfg::K, G = Cfg::G;
+    static constexpr int TXB = Cfg::TXF;                 // same sweep geometry as the forward
+    static constexpr int NCHB = TXB / 8 + 1;
+    static constexpr int ACC_PITCH = TXB + 4;            // 4 * odd
+    static constexpr int U_PLANE = Cfg::ROWS * 8;        // swizzled [row][8]
+    static constexpr int U_WORKER = G * U_PLANE;
+    // edge-pixel region a tile needs: rows [Yb0-P, Yb0+64+P), columns [Xb0-P-8, Xb0+TXB+P)
+    static constexpr int RROWS = Cfg::ROWS + 2 * P;
+    static constexpr int RCOLS = TXB + 2 * P + 8;
+    static constexpr int LIST_STRIDE = RROWS * RCOLS;    // worst case entries per tile
+    static constexpr int LIST_SMEM = 2560;               // entries staged in shared memory
+    static_assert((ACC_PITCH / 4) % 2 == 1, "accumulator rows must be float4 conflict-free");
+};
+
+struct PlaneBwdParams {
+    const void* img;          // SR image [B,3,H,W]
+    const float* gqT;         // [L][cap]
+    const int32_t* tile_cols; // [n_btiles][RCOLS+1] column starts inside the tile's entry list
+    const int32_t* tile_ent;  // [n_btiles][LIST_STRIDE] (slot << 8) | region row
+    float* gpart;             // [NDXG][B][3][HT][WT] partial padded gradients
+    const int32_t* slot_map;
+    int B, H, W, cap;
+    int ntyb, ntxb, HT, WT;
+};
+
+// ---- per-tile edge lists by column ---------------------------------------------------------
+// One block per backward tile.  Entries of a column are in ascending row order.
+template <typename Cfg>
+__global__ void __launch_bounds__(256) plane_bwd_lists_kernel(PlaneBwdParams p, int32_t* tile_cols, int32_t* tile_ent) {
+    using BC = PlaneBwdCfg<Cfg>;
+    constexpr int P = Cfg::P;
+    __shared__ int cnt[BC::RCOLS + 1];
+    const int t = blockIdx.x;
+    const int txb = t % p.ntxb, tyb = (t / p.ntxb) % p.ntyb, b = t / (p.ntxb * p.ntyb);
+    const int y0 = tyb * Cfg::ROWS - P - P;        // image row of region row 0 (padded Yb0-P, minus pad P)
+    const int x0 = txb * BC::TXB - P - 8 - P;      // image column of region column 0
+    for (int i = threadIdx.x; i <= BC::RCOLS; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    // one thread per region column: count, then (after the scan) emit in row order
+    int my = 0;
+    const int col = threadIdx.x;
+    const int x = x0 + col;
+    const bool colok = col < BC::RCOLS && x >= 0 && x < p.W;
+    if (colok)
+        for (int rr = 0; rr < BC::RROWS; ++rr) {
+            const int y = y0 + rr;
+            if (y >= 0 && y < p.H && p.slot_map[(b * p.H + y) * p.W + x] >= 0) ++my;
+        }
+    if (col < BC::RCOLS) cnt[col + 1] = my;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 1; i <= BC::RCOLS; ++i) { run += cnt[i]; cnt[i] = run; }
+    }
+    __syncthreads();
+    int32_t* cols = tile_cols + (long long)t * (BC::RCOLS + 1);
+    for (int i = threadIdx.x; i <= BC::RCOLS; i += blockDim.x) cols[i] = cnt[i];
+    if (colok) {
+        int32_t* ent = tile_ent + (long long)t * BC::LIST_STRIDE + cnt[col];
+        for (int rr = 0; rr < BC::RROWS; ++rr) {
+            const int y = y0 + rr;
+            if (y < 0 || y >= p.H) continue;
+            const int slot = p.slot_map[(b * p.H + y) * p.W + x];
+            if (slot >= 0) *ent++ = (slot << 8) | rr;
+        }
+    }
+}
+
+// swizzled u plane: element (row, col) of a [64][8] plane; float4 reads of a row are conflict-free
+__device__ __forceinline__ int u_index(int row, int col) { return row * 8 + (col ^ (((row >> 2) & 1) << 2)); }
+
+// Place the items of one (plane j, u-column c8) of chunk k: v-direction applied while placing.
+template <typename Cfg>
+__device__ __forceinline__ void place_column(const PlaneBwdParams& p, const int32_t* cols, const int32_t* ent,
+                                             float* uplane, int c8, int xu, int dy, int dx) {
+    using BC = PlaneBwdCfg<Cfg>;
+    constexpr int P = Cfg::P, K = Cfg::K;
+    const int alo = rng_lo(dy, P, K), ahi = rng_hi(dy, P, K);
+    const int blo = rng_lo(dx, P, K), bhi = rng_hi(dx, P, K);
+    const long long row1 = (long long)((dy + P) * Cfg::KS + dx + P) * p.cap;
+    const long long row2 = (long long)((-dy + P) * Cfg::KS + (-dx) + P) * p.cap;
+#pragma unroll
+    for (int kind = 0; kind < 2; ++kind) {
+        // region column holding the edge pixels that land in u-column xu
+        const int pcol = kind == 0 ? xu - blo + P : xu + dx + bhi + P;
+        if (pcol < 0 || pcol >= BC::RCOLS) continue;
+        const int e0 = cols[pcol], e1 = cols[pcol + 1];
+        // rows covered by an entry at region row rr: [rr + lo_off, rr + hi_off] in tile rows
+        const int lo_off = kind == 0 ? -P + alo : -P - dy - ahi;
+        const int hi_off = kind == 0 ? -P + ahi : -P - dy - alo;
+        const float* gq = p.gqT + (kind == 0 ? row1 : row2);
+        for (int e = e0; e < e1; e += 4) {
+            int packed[4];
+            float val[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                packed[m] = e + m < e1 ? ent[e + m] : -1;
+                val[m] = packed[m] >= 0 ? __ldg(gq + (packed[m] >> 8)) : 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                if (packed[m] < 0) continue;
+                const int rr = packed[m] & 255;
+                int r0 = rr + lo_off, r1 = rr + hi_off;
+                r0 = r0 < 0 ? 0 : r0;
+                r1 = r1 > Cfg::ROWS - 1 ? Cfg::ROWS - 1 : r1;
+                for (int rl = r0; rl <= r1; ++rl) uplane[u_index(rl, c8)] += val[m];
+            }
+        }
+    }
+}
+
+// One chunk of the h-direction tree + products for one sweep thread.
+template <typename Cfg, int GI>
+__device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* uworker, int r, int dy, int k,
+                                                float (&wprev)[GroupConsts<Cfg, GI>::GJ][8], float (&acc)[3][8]) {
+    using GC = GroupConsts<Cfg, GI>;
+    constexpr int P = Cfg::P, K = Cfg::K, GJ = GC::GJ, OFF = GC::OFF, NV4 = GC::NV4;
+    float gs[GJ][8];
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) {
+        const int dx = GC::DX0 + j;
+        const int len = rng_hi(dx, P, K) - rng_lo(dx, P, K) + 1;
+        const float* up = uworker + j * PlaneBwdCfg<Cfg>::U_PLANE + r * 8;
+        const int sw = ((r >> 2) & 1) << 2;
+        float w[16], s2[16], s4[16], s8[16];
+        float4 a = *reinterpret_cast<const float4*>(up + (0 ^ sw));
+        float4 b = *reinterpret_cast<const float4*>(up + (4 ^ sw));
+        const float cur[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { w[i] = wprev[j][i]; w[8 + i] = cur[i]; wprev[j][i] = cur[i]; }
+#pragma unroll
+        for (int i = 1; i < 16; ++i) s2[i] = w[i] + w[i - 1];
+#pragma unroll
+        for (int i = 3; i < 16; ++i) s4[i] = s2[i] + s2[i - 2];
+#pragma unroll
+        for (int i = 7; i < 16; ++i) s8[i] = s4[i] + s4[i - 4];
+        s2[0] = s4[0] = s4[1] = s4[2] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) s8[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float s;
+            switch (len) {
+                case 1: s = sum_last<1>(w, s2, s4, s8, 8 + i); break;
+                case 2: s = sum_last<2>(w, s2, s4, s8, 8 + i); break;
+                case 3: s = sum_last<3>(w, s2, s4, s8, 8 + i); break;
+                case 4: s = sum_last<4>(w, s2, s4, s8, 8 + i); break;
+                case 5: s = sum_last<5>(w, s2, s4, s8, 8 + i); break;
+                case 6: s = sum_last<6>(w, s2, s4, s8, 8 + i); break;
+                case 7: s = sum_last<7>(w, s2, s4, s8, 8 + i); break;
+                case 8: s = sum_last<8>(w, s2, s4, s8, 8 + i); break;
+                default: s = sum_last<9>(w, s2, s4, s8, 8 + i); break;
+            }
+            gs[j][i] = s;
+        }
+    }
+    if (k == 0) return;  // chunk 0 only primes the tree (its outputs lie left of the tile)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* rowb = tile + (c * Cfg::IROWS + r + P) * Cfg::IPITCH + Cfg::ICOL0 + 8 * k;
+        const float* rown = tile + (c * Cfg::IROWS + r + P + dy) * Cfg::IPITCH + Cfg::ICOL0 + 8 * k + (GC::DX0 - OFF);
+        float base[8], nb[4 * NV4];
+        *reinterpret_cast<float4*>(&base[0]) = *reinterpret_cast<const float4*>(rowb);
+        *reinterpret_cast<float4*>(&base[4]) = *reinterpret_cast<const float4*>(rowb + 4);
+#pragma unroll
+        for (int v = 0; v < NV4; ++v)
+            *reinterpret_cast<float4*>(&nb[4 * v]) = *reinterpret_cast<const float4*>(rown + 4 * v);
+#pragma unroll
+        for (int j = 0; j < GJ; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(base[i] - nb[OFF + i + j], gs[j][i], acc[c][i]);
+    }
+}
+
+template <typename Cfg, int GI>
+__device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const float* tile, float* ubuf, float* accT,
+                                              const int32_t* cols, const int32_t* ent) {
+    using GC = GroupConsts<Cfg, GI>;
+    using BC = PlaneBwdCfg<Cfg>;
+    constexpr int P = Cfg::P, GJ = GC::GJ, NWP = Cfg::NWP;
+    const int tid = threadIdx.x;
+    const int wp = tid / Cfg::ROWS, r = tid % Cfg::ROWS;
+    float* uworker = ubuf + wp * BC::U_WORKER;
+    constexpr int NDY_MAX = (Cfg::KS + NWP - 1) / NWP;
+    const int n_seq = NDY_MAX * BC::NCHB;
+    // place-side role: (u-column c8, plane pj)
+    const int c8 = r & 7, pj = r >> 3;
+    float wprev[GJ][8];
+    for (int phase = 0; phase < n_seq + NWP - 1; ++phase) {
+        const int n = phase - wp;
+        const int idy = n / BC::NCHB, k = n - idy * BC::NCHB;
+        const int dy = wp - P + idy * NWP;
+        const bool active = n >= 0 && n < n_seq && dy <= P;
+        if (active) {
+            if (k == 0) {
+#pragma unroll
+                for (int j = 0; j < GJ; ++j)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
+            }
+            // 1. clear this worker's u planes
+            for (int i = r; i < GJ * BC::U_PLANE / 4; i += Cfg::ROWS)
+                reinterpret_cast<float4*>(uworker)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            worker_sync(wp);
+            // 2. place the items of the chunk's 8 u-columns
+            if (pj < GJ) place_column<Cfg>(p, cols, ent, uworker + pj * BC::U_PLANE, c8, 8 * k + c8, dy, GC::DX0 + pj);
+            worker_sync(wp);
+            // 3. h-direction + products, 4. add into the accumulator tile (output chunk k-1)
+            float acc[3][8];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+            sweep_chunk_bwd<Cfg, GI>(tile, uworker, r, dy, k, wprev, acc);
+            if (k >= 1) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float4* dst = reinterpret_cast<float4*>(accT + (c * Cfg::ROWS + r) * BC::ACC_PITCH + 8 * (k - 1));
+                    float4 v0 = dst[0], v1 = dst[1];
+                    v0.x += acc[c][0]; v0.y += acc[c][1]; v0.z += acc[c][2]; v0.w += acc[c][3];
+                    v1.x += acc[c][4]; v1.y += acc[c][5]; v1.z += acc[c][6]; v1.w += acc[c][7];
+                    dst[0] = v0; dst[1] = v1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, typename Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(PlaneBwdParams p) {
+    using BC = PlaneBwdCfg<Cfg>;
+    extern __shared__ float4 plane_smem4[];
+    float* tile = reinterpret_cast<float*>(plane_smem4);
+    float* ubuf = tile + 3 * Cfg::IROWS * Cfg::IPITCH;
+    float* accT = ubuf + Cfg::NWP * BC::U_WORKER;
+    int32_t* ent_s = reinterpret_cast<int32_t*>(accT + 3 * Cfg::ROWS * BC::ACC_PITCH);
+    __shared__ int32_t cols_s[BC::RCOLS + 1];
+    const int t = blockIdx.x;
+    const int txb = t % p.ntxb, tyb = (t / p.ntxb) % p.ntyb, b = t / (p.ntxb * p.ntyb);
+    const int32_t* cols_g = p.tile_cols + (long long)t * (BC::RCOLS + 1);
+    const int n_ent = cols_g[BC::RCOLS];
+    float* out = p.gpart + ((long long)blockIdx.y * p.B + b) * 3 * p.HT * p.WT;
+    const int Yb0 = tyb * Cfg::ROWS, Xb0 = txb * BC::TXB;
+    if (n_ent == 0) {  // nothing lands in this tile
+        for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::TXB; i += blockDim.x) {
+            const int xo = i % BC::TXB, rr = (i / BC::TXB) % Cfg::ROWS, c = i / (BC::TXB * Cfg::ROWS);
+            out[((long long)c * p.HT + Yb0 + rr) * p.WT + Xb0 + xo] = 0.f;
+        }
+        return;
+    }
+    const T* img = static_cast<const T*>(p.img) + (long long)b * 3 * p.H * p.W;
+    load_plane_tile<T, Cfg>(img, tile, p.H, p.W, Yb0 - Cfg::P, Xb0 - 8 - Cfg::ICOL0);
+    for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::ACC_PITCH; i += blockDim.x) accT[i] = 0.f;
+    for (int i = threadIdx.x; i <= BC::RCOLS; i += blockDim.x) cols_s[i] = cols_g[i];
+    const int32_t* ent_g = p.tile_ent + (long long)t * BC::LIST_STRIDE;
+    const bool staged = n_ent <= BC::LIST_SMEM;
+    if (staged)
+        for (int i = threadIdx.x; i < n_ent; i += blockDim.x) ent_s[i] = ent_g[i];
+    const int32_t* ent = staged ? ent_s : ent_g;
+    __syncthreads();
+    switch (blockIdx.y) {
+        case 0: run_group_bwd<Cfg, 0>(p, tile, ubuf, accT, cols_s, ent); break;
+        case 1: if constexpr (Cfg::NDXG > 1) run_group_bwd<Cfg, 1>(p, tile, ubuf, accT, cols_s, ent); break;
+        case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, ent); break;
+        case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, ent); break;
+        case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, ent); break;
+        default: break;
+    }
+    // the factor 2 of d(t^2) is applied here, once
+    for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::TXB; i += blockDim.x) {
+        const int xo = i % BC::TXB, rr = (i / BC::TXB) % Cfg::ROWS, c = i / (BC::TXB * Cfg::ROWS);
+        out[((long long)c * p.HT + Yb0 + rr) * p.WT + Xb0 + xo] = 2.f * accT[(c * Cfg::ROWS + rr) * BC::ACC_PITCH + xo];
+    }
+}
+
+template <typename Cfg>
+constexpr size_t plane_bwd_smem_bytes() {
+    using BC = PlaneBwdCfg<Cfg>;
+    return (size_t)(3 * Cfg::IROWS * Cfg::IPITCH + Cfg::NWP * BC::U_WORKER + 3 * Cfg::ROWS * BC::ACC_PITCH) * sizeof(float) +
+           (size_t)BC::LIST_SMEM * sizeof(int32_t);
+}
+
+// ---- out-of-area terms and the reflect-pad adjoint -------------------------------------------
+// wtab[slot][(a+K)*KW + (b+K)] = sum of dL/dq over the classes for which window offset (a,b) is out
+// of area (similarity.cu:123-124: the neighbour is zero there, so only the centre pixel gets 2*I*g).
+template <typename Cfg>
+__global__ void __launch_bounds__(128) plane_wtab_kernel(const float* gcls, const int32_t* counts, int cap, float* wtab) {
+    constexpr int K = Cfg::K, KW = Cfg::KW, NC = Cfg::NCLS;
+    __shared__ float sG[4][NC * NC], sR[4][NC], sT[4][NC * KW];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_slots = min(counts[0], cap);
+    for (int slot = blockIdx.x * 4 + w; slot < n_slots; slot += gridDim.x * 4) {
+        for (int i = lane; i < NC * NC; i += 32) sG[w][i] = gcls[(long long)slot * (NC * NC) + i];
+        __syncwarp();
+        if (lane < NC) {
+            float s = 0.f;
+            for (int cb = 0; cb < NC; ++cb) s += sG[w][lane * NC + cb];
+            sR[w][lane] = s;
+        }
+        for (int i = lane; i < NC * KW; i += 32) {
+            const int ca = i / KW, b = i % KW - K;
+            float s = 0.f;
+            for (int cb = 0; cb < NC; ++cb)
+                if (b < class_lo(cb, K) || b > class_hi(cb, K)) s += sG[w][ca * NC + cb];
+            sT[w][i] = s;
+        }
+        __syncwarp();
+        for (int i = lane; i < KW * KW; i += 32) {
+            const int a = i / KW - K, b = i % KW;
+            float s = 0.f;
+            for (int ca = 0; ca < NC; ++ca) s += (a < class_lo(ca, K) || a > class_hi(ca, K)) ? sR[w][ca] : sT[w][ca * KW + b];
+            wtab[(long long)slot * (KW * KW) + i] = s;
+        }
+        __syncwarp();
+    }
+}
+
+struct PlaneFinishParams {
+    const void* img;
+    const float* gpart;       // [NDXG][B][3][HT][WT]
+    const float* wtab;        // [cap][KW*KW]
+    const int32_t* slot_map;
+    float* grad;              // [B,3,H,W], overwritten
+    int B, H, W, HT, WT, n_parts, cap;
+};
+
+// Padded-domain gradient at (Y,X) of image b, all three channels.
+template <typename T, typename Cfg>
+__device__ __forceinline__ void padded_grad_at(const PlaneFinishParams& p, const T* img, int b, int Y, int X, float (&g)[3]) {
+    constexpr int P = Cfg::P, K = Cfg::K, KW = Cfg::KW;
+    const long long plane = (long long)p.HT * p.WT;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float s = 0.f;
+        for (int part = 0; part < p.n_parts; ++part)
+            s += p.gpart[(((long long)part * p.B + b) * 3 + c) * plane + (long long)Y * p.WT + X];
+        g[c] = s;
+    }
+    // out-of-area weight: every edge pixel p = x - (a,b) within the window reach
+    float wsum = 0.f;
+    for (int a = -K; a <= K; ++a) {
+        const int y = Y - a - P;
+        if (y < 0 || y >= p.H) continue;
+        for (int bb = -K; bb <= K; ++bb) {
+            const int x = X - bb - P;
+            if (x < 0 || x >= p.W) continue;
+            const int slot = p.slot_map[(b * p.H + y) * p.W + x];
+            if (slot >= 0 && slot < p.cap) wsum += p.wtab[(long long)slot * (KW * KW) + (a + K) * KW + bb + K];
+        }
+    }
+    const int sy = reflect_idx(Y - P, p.H), sx = reflect_idx(X - P, p.W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        g[c] = fmaf(2.f * wsum, load_as_float(img + ((long long)c * p.H + sy) * p.W + sx), g[c]);
+}
+
+// Adjoint of F.pad(reflect) (similaritywrapper.py:64) as a gather: an image pixel sums the padded
+// pixels that mirror onto it (at most 2 per axis).
+template <typename T, typename Cfg>
+__global__ void __launch_bounds__(256) plane_finish_kernel(PlaneFinishParams p) {
+    constexpr int P = Cfg::P;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long hw = (long long)p.H * p.W;
+    if (idx >= p.B * hw) return;
+    const int b = (int)(idx / hw), rem = (int)(idx - b * hw), y = rem / p.W, x = rem - y * p.W;
+    const T* img = static_cast<const T*>(p.img) + (long long)b * 3 * hw;
+    int Ys[3], Xs[3], ny = 1, nx = 1;
+    Ys[0] = y + P; Xs[0] = x + P;
+    if (y >= 1 && y <= P) Ys[ny++] = P - y;
+    if (y <= p.H - 2 && y >= p.H - 1 - P) Ys[ny++] = P + 2 * (p.H - 1) - y;
+    if (x >= 1 && x <= P) Xs[nx++] = P - x;
+    if (x <= p.W - 2 && x >= p.W - 1 - P) Xs[nx++] = P + 2 * (p.W - 1) - x;
+    float tot[3] = {0.f, 0.f, 0.f};
+    for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+            float g[3];
+            padded_grad_at<T, Cfg>(p, img, b, Ys[iy], Xs[ix], g);
+            tot[0] += g[0]; tot[1] += g[1]; tot[2] += g[2];
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p.grad[((long long)b * 3 + c) * hw + rem] = tot[c];
+}
+
+}  // namespace sslb

@@ -88,16 +88,26 @@ __global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
 // reflect pad of loss_util.py:189-191 by index mapping, zero outside the padded image.
 template <typename T, typename Cfg>
 __device__ __forceinline__ void load_plane_tile(const T* img, float* tile, int H, int W, int Yrow0, int Xcol0) {
-    constexpr int P = Cfg::P;
+    constexpr int P = Cfg::P, NCOLIT = (Cfg::IPITCH + 31) / 32;
     const int Hp = H + 2 * P, Wp = W + 2 * P;
-    for (int idx = threadIdx.x; idx < 3 * Cfg::IROWS * Cfg::IPITCH; idx += blockDim.x) {
-        const int col = idx % Cfg::IPITCH, rr = idx / Cfg::IPITCH;
-        const int row = rr % Cfg::IROWS, c = rr / Cfg::IROWS;
-        const int Y = Yrow0 + row, X = Xcol0 + col;
-        float v = 0.f;
-        if (Y >= 0 && Y < Hp && X >= 0 && X < Wp)
-            v = load_as_float(img + ((long long)c * H + reflect_idx(Y - P, H)) * W + reflect_idx(X - P, W));
-        tile[idx] = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int sx[NCOLIT];
+#pragma unroll
+    for (int m = 0; m < NCOLIT; ++m) {
+        const int X = Xcol0 + lane + 32 * m;
+        sx[m] = (X >= 0 && X < Wp && lane + 32 * m < Cfg::IPITCH) ? reflect_idx(X - P, W) : -1;
+    }
+    for (int rr = warp; rr < 3 * Cfg::IROWS; rr += nwarps) {
+        const int c = rr / Cfg::IROWS, row = rr - c * Cfg::IROWS;
+        const int Y = Yrow0 + row;
+        const bool rowok = Y >= 0 && Y < Hp;
+        const T* src = img + ((long long)c * H + (rowok ? reflect_idx(Y - P, H) : 0)) * W;
+        float v[NCOLIT];
+#pragma unroll
+        for (int m = 0; m < NCOLIT; ++m) v[m] = (rowok && sx[m] >= 0) ? load_as_float(src + sx[m]) : 0.f;
+#pragma unroll
+        for (int m = 0; m < NCOLIT; ++m)
+            if (lane + 32 * m < Cfg::IPITCH) tile[rr * Cfg::IPITCH + lane + 32 * m] = v[m];
     }
 }
 
@@ -158,7 +168,7 @@ __device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splane
         constexpr int dummy = 0;
         (void)dummy;
         const int dx = GC::DX0 + j;
-        const int bhi = rng_hi(dx, P, K), len = bhi - rng_lo(dx, P, K) + 1;
+        const int len = rng_hi(dx, P, K) - rng_lo(dx, P, K) + 1;
         float w[16], s2[16], s4[16], s8[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { w[i] = wprev[j][i]; w[8 + i] = d[j][i]; wprev[j][i] = d[j][i]; }
@@ -171,7 +181,7 @@ __device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splane
         s2[0] = s4[0] = s4[1] = s4[2] = 0.f;
 #pragma unroll
         for (int i = 0; i < 7; ++i) s8[i] = 0.f;
-        float* sp = splanes + (wp * Cfg::G + j) * Cfg::SPS + r * Cfg::SRP;
+        float* sp = splanes + (wp * Cfg::G + j) * Cfg::SPS + r * Cfg::SRP + (k & 1) * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float s;
@@ -186,35 +196,42 @@ __device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splane
                 case 8: s = sum_last<8>(w, s2, s4, s8, 8 + i); break;
                 default: s = sum_last<9>(w, s2, s4, s8, 8 + i); break;
             }
-            sp[(8 * k + i - bhi + K) & (Cfg::RING - 1)] = s;
+            sp[i] = s;
         }
     }
 }
 
+__device__ __forceinline__ void worker_sync(int wp) {
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + wp) : "memory");
+}
+
+// One worker = one warp pair = 64 image rows of one (dy, dx-group); workers of a CTA only share the
+// image tile.  Per chunk: sweep -> barrier(64) -> gather of the previous chunk's edge pixels ->
+// barrier(64).  In the gather a thread owns (group of 4 slots, plane j).
 template <typename Cfg, int GI>
 __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const float* tile, float* splanes, int unit0,
                                               int which) {
     using GC = GroupConsts<Cfg, GI>;
     constexpr int P = Cfg::P, K = Cfg::K, G = Cfg::G, GJ = GC::GJ, NC = Cfg::NCLS;
-    constexpr int NWARPS = Cfg::THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NGRP = Cfg::ROWS / GJ;  // slot groups handled in parallel by one worker
+    const int tid = threadIdx.x;
     const int wp = tid / Cfg::ROWS, r = tid % Cfg::ROWS;
     float* qT = p.qT[which];
     const float* eout = p.eout[which];
     const int cap = p.cap;
-    for (int dys = 0; dys < Cfg::NDYS; ++dys) {
-        const int dy = dys * Cfg::NWP + wp - P;
-        const bool dy_ok = dy <= P;
-        // gather-side constants of this lane's plane
-        const int pl_wp = lane / G, pl_j = lane % G;
-        const int g_dy = dys * Cfg::NWP + pl_wp - P, g_dx = GC::DX0 + pl_j;
-        const bool pl_ok = lane < Cfg::NPL && g_dy <= P && pl_j < GJ;
-        const int alo = rng_lo(g_dy, P, K), ahi = rng_hi(g_dy, P, K);
-        const int ca = clip_class(g_dy, P, K), cb = clip_class(g_dx, P, K);
+    // gather-side role of this thread
+    const int gj = r % GJ, ggrp = r / GJ;
+    const bool g_ok = ggrp < NGRP;
+    const int g_dx = GC::DX0 + gj;
+    const int cb = clip_class(g_dx, P, K);
+    const int coff = K + rng_hi(g_dx, P, K);
+    const float* myplane = splanes + (wp * G + gj) * Cfg::SPS;
+    for (int dy = wp - P; dy <= P; dy += Cfg::NWP) {
+        const int alo = rng_lo(dy, P, K), ahi = rng_hi(dy, P, K);
+        const int ca = clip_class(dy, P, K);
         const bool clipped = ca != K || cb != K;
         const int cls = ca * NC + cb;
-        const long long qrow = (long long)((g_dy + P) * Cfg::KS + g_dx + P) * cap;
-        const float* myplane = splanes + lane * Cfg::SPS;
+        const long long qrow = (long long)((dy + P) * Cfg::KS + g_dx + P) * cap;
 
         float wprev[GJ][8];
 #pragma unroll
@@ -223,15 +240,14 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
             for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
 
         for (int k = 0; k < Cfg::NCH; ++k) {
-            if (dy_ok) sweep_chunk_fwd<Cfg, GI>(tile, splanes, r, dy, wp, k, wprev);
-            __syncthreads();
-            if (k >= 1) {
+            sweep_chunk_fwd<Cfg, GI>(tile, splanes, r, dy, wp, k, wprev);
+            worker_sync(wp);
+            if (k >= 1 && g_ok) {
                 const int u = unit0 + k - 1;
                 const int s0 = p.lists.unit_start[u];
                 const int s1 = min(p.lists.unit_start[u + 1], cap);
-                for (int gs = s0 + 4 * warp; gs < s1; gs += 4 * NWARPS) {
+                for (int gs = s0 + 4 * ggrp; gs < s1; gs += 4 * NGRP) {
                     const int4 rc4 = *reinterpret_cast<const int4*>(p.lists.slot_rc + gs);
-                    if (!pl_ok) continue;
                     const int rcs[4] = {rc4.x, rc4.y, rc4.z, rc4.w};
                     float out[4];
 #pragma unroll
@@ -240,7 +256,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
                         float acc = 0.f;
                         if (rc >= 0) {
                             const int re = rc >> 8, ex = rc & 255;
-                            const float* sp = myplane + re * Cfg::SRP + ((ex + 2 * K) & (Cfg::RING - 1));
+                            const float* sp = myplane + re * Cfg::SRP + ((ex + coff) & (Cfg::RING - 1));
 #pragma unroll
                             for (int a = -K; a <= K; ++a)
                                 if (a >= alo && a <= ahi) acc += sp[a * Cfg::SRP];
@@ -251,7 +267,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
                     *reinterpret_cast<float4*>(qT + qrow + gs) = make_float4(out[0], out[1], out[2], out[3]);
                 }
             }
-            __syncthreads();
+            worker_sync(wp);
         }
     }
 }

@@ -336,27 +336,57 @@ __global__ void set_terms_count_kernel(const int32_t* counts, double* terms) { t
 
 }  // namespace
 
-extern "C" size_t ssl_b200_loss_workspace_bytes(int ks, int max_edges) {
+namespace {
+
+size_t point_loss_workspace_bytes(int ks, int max_edges) {
     const size_t rows = align256((size_t)(max_edges > 0 ? max_edges : 1) * ks * ks * sizeof(float));
     return 2 * rows + align256(2 * sizeof(double) * (size_t)ssl_b200_row_loss_blocks());
+}
+
+// Plane kernels pay per image pixel, point kernels per edge pixel: below ~2 % density the point
+// kernels win (measured crossover, profiles/).
+bool use_plane_path(int path, int B, int C, int H, int W, int ks, int kw, int max_edges) {
+    if (path == SSL_B200_PATH_POINT || !plane_supported(ks, kw, C)) return false;
+    if (path == SSL_B200_PATH_PLANE) return true;
+    return (double)max_edges >= 0.02 * (double)B * H * W;
+}
+
+}  // namespace
+
+extern "C" size_t ssl_b200_loss_workspace_bytes(int B, int C, int H, int W, int ks, int kw, int max_edges, int path) {
+    if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
+    if (!use_plane_path(path, B, C, H, W, ks, kw, max_edges)) return point_loss_workspace_bytes(ks, max_edges);
+    DeviceInfo di;
+    const int loss_blocks = device_info(&di) ? 148 : di.sm_count;
+    SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, { return plane_step_layout<Cfg>(B, H, W, max_edges, loss_blocks, true).total; });
 }
 
 extern "C" int ssl_b200_loss_forward_backward(const void* sr, const void* gt, int dtype, int B, int C, int H, int W,
                                               const int32_t* edges, const int32_t* counts, int max_edges, int ks,
                                               int kw, float sigma, float eps, int rows_mode, float w_l1, float w_kl,
                                               float* grad_sr, double* terms, void* workspace, size_t workspace_bytes,
-                                              void* stream) {
+                                              int path, void* stream) {
     SSLB_REQUIRE(sr && gt && edges && counts && terms && workspace, "null pointer");
     SSLB_REQUIRE(rows_mode == SSL_B200_ROWS_EXP || rows_mode == SSL_B200_ROWS_NORM,
                  "the loss is defined on exp / normalised rows");
-    SSLB_REQUIRE(workspace_bytes >= ssl_b200_loss_workspace_bytes(ks, max_edges), "workspace too small");
+    SSLB_REQUIRE(workspace_bytes >= ssl_b200_loss_workspace_bytes(B, C, H, W, ks, kw, max_edges, path),
+                 "workspace too small");
+    SSLB_REQUIRE(path != SSL_B200_PATH_PLANE || plane_supported(ks, kw, C), "no plane kernels for k_s=%d k_w=%d C=%d",
+                 ks, kw, C);
     if (int e = check_sizes(ks, kw, H, W, C)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     SSLB_CUDA(cudaMemsetAsync(terms, 0, 3 * sizeof(double), st));
-    if (grad_sr) SSLB_CUDA(cudaMemsetAsync(grad_sr, 0, sizeof(float) * (size_t)B * C * H * W, st));
+    const bool plane = max_edges > 0 && use_plane_path(path, B, C, H, W, ks, kw, max_edges);
+    if (grad_sr && !plane) SSLB_CUDA(cudaMemsetAsync(grad_sr, 0, sizeof(float) * (size_t)B * C * H * W, st));
     set_terms_count_kernel<<<1, 1, 0, st>>>(counts, terms);
     if (int e = check_launch("set_terms_count")) return e;
     if (max_edges <= 0) return 0;
+    if (plane) {
+        SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, {
+            return launch_plane_step_cfg<Cfg>(sr, gt, dtype, B, H, W, edges, counts, max_edges, sigma, eps, rows_mode,
+                                              w_l1, w_kl, grad_sr, terms, workspace, workspace_bytes, st);
+        });
+    }
     const size_t rows_bytes = align256((size_t)max_edges * ks * ks * sizeof(float));
     char* ws = static_cast<char*>(workspace);
     float* rows_sr = reinterpret_cast<float*>(ws);
@@ -434,7 +464,7 @@ extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_hos
     const size_t fixed = 3 * img_bytes + mask_bytes + edges_bytes + counts_bytes + el_ws + small_bytes;
     // first pass with the arena we have (or the fixed part); rows need the edge count
     HostArena& a = arena();
-    if (int e = arena_reserve(fixed + ssl_b200_loss_workspace_bytes(ks, (int)(n_px / 8 + 1)))) return e;
+    if (int e = arena_reserve(fixed + ssl_b200_loss_workspace_bytes(B, C, H, W, ks, kw, (int)(n_px / 8 + 1), 0))) return e;
     auto carve = [&](char*& p, size_t b) { char* r = p; p += b; return r; };
     char* p = a.base;
     float* d_mask = (float*)carve(p, mask_bytes);
@@ -466,7 +496,7 @@ extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_hos
     cudaEventDestroy(counted);
     if (ce != cudaSuccess) return fail((int)ce, "edge count readback: %s", cudaGetErrorString(ce));
     const int n_rows = a.counts_pinned[0];
-    const size_t ws_bytes = ssl_b200_loss_workspace_bytes(ks, n_rows);
+    const size_t ws_bytes = ssl_b200_loss_workspace_bytes(B, C, H, W, ks, kw, n_rows, 0);
     if (fixed + ws_bytes > a.bytes) {
         // grow (rare: first call, or a denser mask than ever seen) and redo the uploads
         if (int e = arena_reserve(fixed + ws_bytes + ws_bytes / 4)) return e;
@@ -478,7 +508,7 @@ extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_hos
     float* d_inv_n = (float*)(d_small + 128);
     if (int e = ssl_b200_loss_forward_backward(d_sr, d_gt, SSL_B200_F32, B, C, H, W, d_edges, d_counts, n_rows, ks, kw,
                                                sigma, eps, rows_mode, w_l1, w_kl, grad_host ? d_grad : nullptr,
-                                               d_terms, d_ws, ws_bytes, stream)) return e;
+                                               d_terms, d_ws, ws_bytes, SSL_B200_PATH_AUTO, stream)) return e;
     finalize_loss_kernel<<<1, 1, 0, st>>>(d_terms, ks * ks, w_l1, w_kl, d_loss, d_inv_n);
     if (int e = check_launch("finalize_loss")) return e;
     SSLB_CUDA(cudaMemcpyAsync(loss_host, d_loss, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));

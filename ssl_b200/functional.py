@@ -209,7 +209,7 @@ class _SSLLoss(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, sr, gt, el, n, ks, kw, sigma, eps, mode, w_l1, w_kl, reducer):
+    def forward(ctx, sr, gt, el, n, ks, kw, sigma, eps, mode, w_l1, w_kl, reducer, path=0):
         sr_c, gt_c = sr.contiguous(), gt.contiguous()
         if gt_c.dtype != sr_c.dtype:
             gt_c = gt_c.to(sr_c.dtype)
@@ -218,13 +218,13 @@ class _SSLLoss(torch.autograd.Function):
         c = sr_c.shape[1]
         terms = torch.empty(3, dtype=torch.float64, device=dev)   # sum|d|, sum KL, n_rows
         grad = torch.empty(sr_c.shape, dtype=torch.float32, device=dev) if need_grad else None
-        ws_bytes = int(_lib.load().ssl_b200_loss_workspace_bytes(ks, n))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         b, _, h, w = sr_c.shape
+        ws_bytes = int(_lib.load().ssl_b200_loss_workspace_bytes(b, c, h, w, ks, kw, n, int(path)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.call("ssl_b200_loss_forward_backward", _ptr(sr_c), _ptr(gt_c), _lib.dtype_code(sr_c.dtype), b, c, h, w,
                       _ptr(el.edges), _ptr(el.counts), n, ks, kw, float(sigma), float(eps), mode, float(w_l1),
-                      float(w_kl), _ptr(grad), _ptr(terms), _ptr(ws), ws_bytes, _stream())
+                      float(w_kl), _ptr(grad), _ptr(terms), _ptr(ws), ws_bytes, int(path), _stream())
         if reducer is not None:
             terms = reducer(terms)
         n_tot = (terms[2] * (ks * ks)).clamp_min(1.0)
@@ -243,9 +243,9 @@ class _SSLLoss(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_total, _g_l1, _g_kl):
         if ctx.grad_sr is None:
-            return (None,) * 12
+            return (None,) * 13
         g = (ctx.grad_sr * (g_total.to(torch.float32) * ctx.inv_n)).to(ctx.sr_dtype)
-        return (g,) + (None,) * 11
+        return (g,) + (None,) * 12
 
 
 def ssl_step_host(sr, gt, mask, kernel_size_search: int = 25, kernel_size_window: int = 9, sigma: float = 0.004,

@@ -17,10 +17,14 @@ from . import functional as F_
 from .dist import make_reducer
 
 
+_PATHS = {"auto": 0, "point": 1, "plane": 2}
+
+
 def ssl(sr: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None, kernel_size_search: int = 25,
         kernel_size_window: int = 9, sigma: float = 0.004, generalization: bool = True, eps: float = 1e-10,
         loss_weight: float = 1.0, kl_weight: float = 0.0, mask_stride: int = 0, mask_threshold: float = 20.0,
-        max_edges: Optional[int] = None, parity: str = "global", group=None, return_parts: bool = False):
+        max_edges: Optional[int] = None, parity: str = "global", group=None, return_parts: bool = False,
+        path: str = "auto"):
     """Self-similarity loss of a batch.
 
     sr, gt : [B,C,H,W] CUDA tensors (fp32 / bf16 / fp16); gradients flow into ``sr`` only
@@ -31,6 +35,7 @@ def ssl(sr: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None,
     the reference's ``l_selfsim`` and ``l_selfsim_kl``; with ``return_parts`` also the two terms
     (detached, for the loss dict).  An all-empty mask gives 0 (the reference omits the term).
     ``max_edges`` (rows capacity) makes the call free of host syncs and CUDA-graph capturable.
+    ``path``: "auto" | "point" | "plane" -- which kernels run (include/ssl_b200.h SSL_B200_PATH_*).
     """
     F_._require_cuda(sr, "sr")
     F_._require_cuda(gt, "gt")
@@ -47,7 +52,7 @@ def ssl(sr: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None,
     mode = F_.rows_mode(generalization)
     total, l1, kl = F_._SSLLoss.apply(sr, gt.detach(), el, n, int(kernel_size_search), int(kernel_size_window),
                                       float(sigma), float(eps), mode, float(loss_weight), float(kl_weight),
-                                      make_reducer(parity, group))
+                                      make_reducer(parity, group), _PATHS[path])
     return (total, l1, kl) if return_parts else total
 
 
@@ -58,8 +63,9 @@ class SelfSimilarityLoss(nn.Module):
     def __init__(self, kernel_size_search: int = 25, kernel_size_window: int = 9, sigma: float = 0.004,
                  generalization: bool = True, eps: float = 1e-10, loss_weight: float = 1.0, kl_weight: float = 0.0,
                  mask_stride: int = 0, mask_threshold: float = 20.0, max_edges: Optional[int] = None,
-                 parity: str = "global"):
+                 parity: str = "global", path: str = "auto"):
         super().__init__()
+        self.path = path
         self.kernel_size_search = kernel_size_search
         self.kernel_size_window = kernel_size_window
         self.sigma = sigma
@@ -78,7 +84,7 @@ class SelfSimilarityLoss(nn.Module):
         total, self.last_l1, self.last_kl = ssl(
             sr, gt, mask, self.kernel_size_search, self.kernel_size_window, self.sigma, self.generalization, self.eps,
             self.loss_weight, self.kl_weight, self.mask_stride, self.mask_threshold, self.max_edges, self.parity,
-            return_parts=True)
+            return_parts=True, path=self.path)
         return total
 
     def extra_repr(self) -> str:
