@@ -46,6 +46,7 @@ struct PlaneCfg {
     static constexpr int RING = 16;
     static constexpr int SRP = RING + 1;                 // odd row pitch
     static constexpr int SPS = (ROWS * SRP) | 1;         // odd plane stride
+    static constexpr int RC_SMEM = 2048;                 // slot descriptors of a tile staged in shared memory
     static_assert(KS % 2 == 1 && KW % 2 == 1 && KW <= KS && KW <= 9, "unsupported kernel sizes");
     static_assert(NPL <= 32, "one lane per plane");
     static_assert(2 * K <= CH, "gather lags the sweep by one chunk");

@@ -22,11 +22,11 @@ struct RowLossTParams {
     float denom, sigma, eps, chain;
     int mode, want_grad;
     float w_l1, w_kl;
-    float* gcls;           // [cap][(2K+1)^2] or NULL
+    float* gcls;           // [(2K+1)^2][cap] or NULL
     double* scratch;       // [2 * gridDim.x]
 };
 
-constexpr int kRowTThreads = 256;
+constexpr int kRowTThreads = 512;
 constexpr int kRowTPhases = kRowTThreads / 32;
 
 __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams p) {
@@ -41,18 +41,31 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
     for (int slot0 = blockIdx.x * 32; slot0 < n_slots; slot0 += gridDim.x * 32) {
         const int slot = slot0 + s;
         const bool valid = slot < n_slots && p.slot_pix[slot] >= 0;
-        // pass 1: e = exp(-1 * (q / (C kw^2)) / sigma), partial row sums
+        // pass 1: e = exp(-1 * (q / (C kw^2)) / sigma), partial row sums.  Loads are issued in batches
+        // of 2*UN so that enough bytes are in flight to cover the HBM latency.
         float zs = 0.f, zt = 0.f;
-        for (int d = ph; d < p.L; d += kRowTPhases) {
-            float a = 0.f, b = 0.f;
-            if (valid) {
-                a = expf(-1.0f * (p.qs[(long long)d * p.cap + slot] / p.denom) / p.sigma);
-                b = expf(-1.0f * (p.qg[(long long)d * p.cap + slot] / p.denom) / p.sigma);
+        constexpr int UN = 8;
+        for (int d0 = ph; d0 < p.L; d0 += kRowTPhases * UN) {
+            float qa[UN], qb[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int d = d0 + u * kRowTPhases;
+                const bool ok = valid && d < p.L;
+                qa[u] = ok ? __ldcs(p.qs + (long long)d * p.cap + slot) : 0.f;
+                qb[u] = ok ? __ldcs(p.qg + (long long)d * p.cap + slot) : 0.f;
             }
-            es[d * 32 + s] = a;
-            et[d * 32 + s] = b;
-            zs += a;
-            zt += b;
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int d = d0 + u * kRowTPhases;
+                if (d < p.L) {
+                    const float a = valid ? expf(-1.0f * (qa[u] / p.denom) / p.sigma) : 0.f;
+                    const float b = valid ? expf(-1.0f * (qb[u] / p.denom) / p.sigma) : 0.f;
+                    es[d * 32 + s] = a;
+                    et[d * 32 + s] = b;
+                    zs += a;
+                    zt += b;
+                }
+            }
         }
         red[0][ph][s] = zs;
         red[1][ph][s] = zt;
@@ -113,7 +126,7 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
                         for (int dy = dy0; dy <= dy1; ++dy)
                             for (int dx = dx0; dx <= dx1; ++dx) acc += es[((dy + p.P) * p.KS + dx + p.P) * 32 + s];
                     }
-                    p.gcls[(long long)slot * (NC * NC) + c] = acc;
+                    p.gcls[(long long)c * p.cap + slot] = acc;
                 }
             }
         }

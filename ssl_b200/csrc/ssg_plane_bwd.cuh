@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128) plane_wtab_kernel(const float* gcls, cons
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_slots = min(counts[0], cap);
     for (int slot = blockIdx.x * 4 + w; slot < n_slots; slot += gridDim.x * 4) {
-        for (int i = lane; i < NC * NC; i += 32) sG[w][i] = gcls[(long long)slot * (NC * NC) + i];
+        for (int i = lane; i < NC * NC; i += 32) sG[w][i] = gcls[(long long)i * cap + slot];
         __syncwarp();
         if (lane < NC) {
             float s = 0.f;

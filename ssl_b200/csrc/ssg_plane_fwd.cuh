@@ -209,8 +209,8 @@ __device__ __forceinline__ void worker_sync(int wp) {
 // image tile.  Per chunk: sweep -> barrier(64) -> gather of the previous chunk's edge pixels ->
 // barrier(64).  In the gather a thread owns (group of 4 slots, plane j).
 template <typename Cfg, int GI>
-__device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const float* tile, float* splanes, int unit0,
-                                              int which) {
+__device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const float* tile, float* splanes,
+                                              const int32_t* ustart, const int32_t* slot_rc, int which) {
     using GC = GroupConsts<Cfg, GI>;
     constexpr int P = Cfg::P, K = Cfg::K, G = Cfg::G, GJ = GC::GJ, NC = Cfg::NCLS;
     constexpr int NGRP = Cfg::ROWS / GJ;  // slot groups handled in parallel by one worker
@@ -219,6 +219,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
     float* qT = p.qT[which];
     const float* eout = p.eout[which];
     const int cap = p.cap;
+    const int slot0 = ustart[0];  // slot_rc is indexed relative to the tile's first slot
     // gather-side role of this thread
     const int gj = r % GJ, ggrp = r / GJ;
     const bool g_ok = ggrp < NGRP;
@@ -240,15 +241,26 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
             for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
 
         for (int k = 0; k < Cfg::NCH; ++k) {
+            // Out-of-area terms of the first slot group this thread will gather after the sweep:
+            // issued now so that the global-memory latency hides behind the sweep arithmetic.
+            const int s0 = k >= 1 ? ustart[k - 1] : 0;
+            const int s1 = k >= 1 ? min(ustart[k], cap) : 0;
+            float eo[4] = {0.f, 0.f, 0.f, 0.f};
+            const int gs_first = s0 + 4 * ggrp;
+            if (clipped && g_ok && gs_first < s1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) eo[e] = __ldg(eout + (long long)(gs_first + e) * (NC * NC) + cls);
+            }
             sweep_chunk_fwd<Cfg, GI>(tile, splanes, r, dy, wp, k, wprev);
             worker_sync(wp);
-            if (k >= 1 && g_ok) {
-                const int u = unit0 + k - 1;
-                const int s0 = p.lists.unit_start[u];
-                const int s1 = min(p.lists.unit_start[u + 1], cap);
-                for (int gs = s0 + 4 * ggrp; gs < s1; gs += 4 * NGRP) {
-                    const int4 rc4 = *reinterpret_cast<const int4*>(p.lists.slot_rc + gs);
+            if (g_ok) {
+                for (int gs = gs_first; gs < s1; gs += 4 * NGRP) {
+                    const int4 rc4 = *reinterpret_cast<const int4*>(slot_rc + (gs - slot0));
                     const int rcs[4] = {rc4.x, rc4.y, rc4.z, rc4.w};
+                    if (gs != gs_first && clipped) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) eo[e] = __ldg(eout + (long long)(gs + e) * (NC * NC) + cls);
+                    }
                     float out[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -260,7 +272,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
 #pragma unroll
                             for (int a = -K; a <= K; ++a)
                                 if (a >= alo && a <= ahi) acc += sp[a * Cfg::SRP];
-                            if (clipped) acc += __ldg(eout + (long long)(gs + e) * (NC * NC) + cls);
+                            acc += eo[e];
                         }
                         out[e] = acc;
                     }
@@ -277,29 +289,40 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(PlaneFwd
     extern __shared__ float4 plane_smem4[];
     float* tile = reinterpret_cast<float*>(plane_smem4);
     float* splanes = tile + 3 * Cfg::IROWS * Cfg::IPITCH;
+    int32_t* rc_s = reinterpret_cast<int32_t*>(splanes + Cfg::NPL * Cfg::SPS + 3);  // keep 16-byte alignment below
+    rc_s = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(rc_s) + 15) & ~(uintptr_t)15);
+    __shared__ int32_t ustart_s[Cfg::UNITS_X + 1];
     const int t = blockIdx.x;
     const int tx = t % p.g.ntx, ty = (t / p.g.ntx) % p.g.nty, b = t / (p.g.ntx * p.g.nty);
     const int unit0 = t * Cfg::UNITS_X;
-    if (p.lists.unit_start[unit0] >= min(p.lists.unit_start[unit0 + Cfg::UNITS_X], p.cap)) return;  // no edge pixel here
+    const int slot0 = p.lists.unit_start[unit0];
+    const int slot1 = min(p.lists.unit_start[unit0 + Cfg::UNITS_X], p.cap);
+    if (slot0 >= slot1) return;  // no edge pixel in this tile
     const int which = blockIdx.z;
     const T* img = static_cast<const T*>(p.img[which]) + (long long)b * 3 * p.g.H * p.g.W;
     // padded coordinates of the tile's first edge-pixel position: (P + ty*TYF, P + tx*TXF)
     load_plane_tile<T, Cfg>(img, tile, p.g.H, p.g.W, Cfg::P + ty * Cfg::TYF - Cfg::K - Cfg::P,
                             Cfg::P + tx * Cfg::TXF - Cfg::K - Cfg::ICOL0);
+    if (threadIdx.x <= Cfg::UNITS_X) ustart_s[threadIdx.x] = p.lists.unit_start[unit0 + threadIdx.x];
+    const bool staged = slot1 - slot0 <= Cfg::RC_SMEM;
+    if (staged)
+        for (int i = threadIdx.x; i < slot1 - slot0; i += blockDim.x) rc_s[i] = p.lists.slot_rc[slot0 + i];
+    const int32_t* slot_rc = staged ? rc_s : p.lists.slot_rc + slot0;
     __syncthreads();
     switch (blockIdx.y) {
-        case 0: run_group_fwd<Cfg, 0>(p, tile, splanes, unit0, which); break;
-        case 1: if constexpr (Cfg::NDXG > 1) run_group_fwd<Cfg, 1>(p, tile, splanes, unit0, which); break;
-        case 2: if constexpr (Cfg::NDXG > 2) run_group_fwd<Cfg, 2>(p, tile, splanes, unit0, which); break;
-        case 3: if constexpr (Cfg::NDXG > 3) run_group_fwd<Cfg, 3>(p, tile, splanes, unit0, which); break;
-        case 4: if constexpr (Cfg::NDXG > 4) run_group_fwd<Cfg, 4>(p, tile, splanes, unit0, which); break;
+        case 0: run_group_fwd<Cfg, 0>(p, tile, splanes, ustart_s, slot_rc, which); break;
+        case 1: if constexpr (Cfg::NDXG > 1) run_group_fwd<Cfg, 1>(p, tile, splanes, ustart_s, slot_rc, which); break;
+        case 2: if constexpr (Cfg::NDXG > 2) run_group_fwd<Cfg, 2>(p, tile, splanes, ustart_s, slot_rc, which); break;
+        case 3: if constexpr (Cfg::NDXG > 3) run_group_fwd<Cfg, 3>(p, tile, splanes, ustart_s, slot_rc, which); break;
+        case 4: if constexpr (Cfg::NDXG > 4) run_group_fwd<Cfg, 4>(p, tile, splanes, ustart_s, slot_rc, which); break;
         default: break;
     }
 }
 
 template <typename Cfg>
 constexpr size_t plane_fwd_smem_bytes() {
-    return (size_t)(3 * Cfg::IROWS * Cfg::IPITCH + Cfg::NPL * Cfg::SPS) * sizeof(float);
+    return (size_t)(3 * Cfg::IROWS * Cfg::IPITCH + Cfg::NPL * Cfg::SPS + 8) * sizeof(float) +
+           (size_t)Cfg::RC_SMEM * sizeof(int32_t);
 }
 
 // qT[d][slot] -> rows[i][d] in the reference's row order (i = position in the flat edge list).
