@@ -164,6 +164,16 @@ int ssl_b200_loss_step_host(const float* sr_host, const float* gt_host, const fl
 /* Frees the cached arena of the current device. */
 int ssl_b200_release_host_arena(void);
 
+/* Optional per-stage timing of the entry points above.  While enabled, every stage (edge list,
+ * plane lists, forward, row loss, backward, ...) is bracketed by CUDA events recorded on the stream
+ * it is launched on; ssl_b200_profile_read() waits for them and returns, per stage, the summed
+ * milliseconds and the number of bracketed launches since the last read.  Arrays hold
+ * ssl_b200_profile_num_stages() entries.  Not thread safe; meant for benchmarks. */
+int ssl_b200_profile_enable(int on);
+int ssl_b200_profile_num_stages(void);
+const char* ssl_b200_profile_stage_name(int i);
+int ssl_b200_profile_read(float* ms, int* launches);
+
 /* Number of kernels this library has launched in this process so far (all threads). */
 uint64_t ssl_b200_launch_count(void);
 

@@ -53,6 +53,10 @@ SIGNATURES = {
                                          _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_float, _c_float,
                                          _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ssl_b200_release_host_arena": (_c_int, []),
+    "ssl_b200_profile_enable": (_c_int, [_c_int]),
+    "ssl_b200_profile_num_stages": (_c_int, []),
+    "ssl_b200_profile_stage_name": (ctypes.c_char_p, [_c_int]),
+    "ssl_b200_profile_read": (_c_int, [_c_void_p, _c_void_p]),
     "ssl_b200_launch_count": (ctypes.c_uint64, []),
     "ssl_b200_laplacian_mask": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p]),
 }
@@ -90,6 +94,20 @@ def call(name: str, *args) -> None:
     if rc != 0:
         msg = lib.ssl_b200_last_error()
         raise SSLB200Error(f"{name} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def profile_enable(on: bool) -> None:
+    call("ssl_b200_profile_enable", 1 if on else 0)
+
+
+def profile_read() -> dict:
+    """{stage name: (milliseconds, bracketed launches)} since the last read (waits for the events)."""
+    lib = load()
+    n = lib.ssl_b200_profile_num_stages()
+    ms = (ctypes.c_float * n)()
+    cnt = (ctypes.c_int * n)()
+    call("ssl_b200_profile_read", ctypes.cast(ms, _c_void_p), ctypes.cast(cnt, _c_void_p))
+    return {lib.ssl_b200_profile_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
 
 def dtype_code(dtype) -> int:

@@ -41,6 +41,55 @@ inline int check_launch(const char* what, int n_kernels = 1) {
     return 0;
 }
 
+// ---- optional per-stage timing (ssl_b200_profile_*) ------------------------------------------
+// When enabled, every stage of the whole-step entry points is bracketed by CUDA events recorded on
+// the launching stream; bench.py reads the per-stage milliseconds of the very launches it timed.
+enum Stage {
+    kStageEdgeList = 0, kStagePlaneLists, kStageEout, kStagePlaneFwd, kStageRowLoss, kStagePlaneBwdLists,
+    kStagePlaneBwd, kStageFinish, kStagePointFwd, kStagePointBwd, kNumStages
+};
+
+inline const char* stage_name(int i) {
+    static const char* names[kNumStages] = {"edge_list", "plane_lists", "plane_eout", "ssg_plane_fwd", "row_loss",
+                                            "plane_bwd_lists", "ssg_plane_bwd", "plane_finish", "ssg_point_fwd",
+                                            "ssg_point_bwd"};
+    return i >= 0 && i < kNumStages ? names[i] : "?";
+}
+
+struct Profiler {
+    static constexpr int kMaxRecords = 4096;
+    bool enabled = false;
+    int n = 0;
+    cudaEvent_t start[kMaxRecords], stop[kMaxRecords];
+    int stage[kMaxRecords];
+    bool created[kMaxRecords] = {};
+};
+
+inline Profiler& profiler() {
+    static Profiler p;
+    return p;
+}
+
+struct StageTimer {
+    int idx = -1;
+    cudaStream_t st;
+    StageTimer(int stage, cudaStream_t s) : st(s) {
+        Profiler& p = profiler();
+        if (!p.enabled || p.n >= Profiler::kMaxRecords) return;
+        idx = p.n++;
+        if (!p.created[idx]) {
+            cudaEventCreate(&p.start[idx]);
+            cudaEventCreate(&p.stop[idx]);
+            p.created[idx] = true;
+        }
+        p.stage[idx] = stage;
+        cudaEventRecord(p.start[idx], st);
+    }
+    ~StageTimer() {
+        if (idx >= 0) cudaEventRecord(profiler().stop[idx], st);
+    }
+};
+
 #define SSLB_REQUIRE(cond, ...)                                   \
     do {                                                          \
         if (!(cond)) return sslb::fail(SSL_B200_EINVAL, __VA_ARGS__); \

@@ -73,6 +73,7 @@ inline int launch_plane_lists(const float* mask, int mask_channels, int stride, 
     p.edges = edges; p.n_edges_dev = n_edges_dev; p.max_edges = max_edges;
     p.g = g; p.capacity = cap;
     p.out = carve_lists(ws, lay, &p.unit_count);
+    StageTimer timer(kStagePlaneLists, st);
     SSLB_CUDA(cudaMemsetAsync(p.out.counts, 0, 4 * sizeof(int32_t), st));
     const long long npx = (long long)g.B * g.H * g.W;
     const int fill_blocks = (int)((npx + 255) / 256 < 4096 ? (npx + 255) / 256 : 4096);
@@ -101,9 +102,13 @@ inline int launch_plane_forward_cfg(const void* img, const void* img2, int dtype
     SSLB_REQUIRE(smem <= (size_t)di.max_smem_optin, "plane forward needs %zu B of shared memory", smem);
     const int tiles = g.B * g.nty * g.ntx;
     SSLB_DISPATCH_DTYPE(dtype, T, {
-        plane_eout_kernel<T, Cfg><<<dim3(di.sm_count * 8, n_img), 128, 0, st>>>(p);
+        {
+            StageTimer timer(kStageEout, st);
+            plane_eout_kernel<T, Cfg><<<dim3(di.sm_count * 8, n_img), 128, 0, st>>>(p);
+        }
         auto k = ssg_plane_fwd_kernel<T, Cfg>;
         SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        StageTimer timer(kStagePlaneFwd, st);
         k<<<dim3(tiles, Cfg::NDXG, n_img), Cfg::THREADS, smem, st>>>(p);
     });
     return check_launch("plane_forward", 2);
@@ -180,8 +185,11 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
     rp.scratch = reinterpret_cast<double*>(ws + l.off_scratch);
     const size_t rl_smem = (size_t)2 * Cfg::L * 32 * sizeof(float);
     SSLB_CUDA(cudaFuncSetAttribute(row_loss_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl_smem));
-    row_loss_t_kernel<<<loss_blocks, kRowTThreads, rl_smem, st>>>(rp);
-    row_loss_finalize_kernel<<<1, 32, 0, st>>>(rp.scratch, loss_blocks, terms);
+    {
+        StageTimer timer(kStageRowLoss, st);
+        row_loss_t_kernel<<<loss_blocks, kRowTThreads, rl_smem, st>>>(rp);
+        row_loss_finalize_kernel<<<1, 32, 0, st>>>(rp.scratch, loss_blocks, terms);
+    }
     if (int e = check_launch("row_loss_t", 2)) return e;
     if (!grad_sr) return 0;
     PlaneBwdParams bp{};
@@ -193,20 +201,27 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
     bp.slot_map = lists.slot_map;
     bp.B = B; bp.H = H; bp.W = W; bp.cap = l.cap;
     bp.ntyb = l.ntyb; bp.ntxb = l.ntxb; bp.HT = l.HT; bp.WT = l.WT;
-    plane_bwd_lists_kernel<Cfg><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tent);
+    {
+        StageTimer timer(kStagePlaneBwdLists, st);
+        plane_bwd_lists_kernel<Cfg><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tent);
+    }
     const size_t smem = plane_bwd_smem_bytes<Cfg>();
     SSLB_REQUIRE(smem <= (size_t)di.max_smem_optin, "plane backward needs %zu B of shared memory", smem);
     PlaneFinishParams fp{};
     fp.img = sr; fp.gpart = bp.gpart; fp.wtab = reinterpret_cast<float*>(ws + l.off_wtab);
     fp.slot_map = lists.slot_map; fp.grad = grad_sr;
     fp.B = B; fp.H = H; fp.W = W; fp.HT = l.HT; fp.WT = l.WT; fp.n_parts = Cfg::NDXG; fp.cap = l.cap;
-    plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(rp.gcls, lists.counts, l.cap,
-                                                           reinterpret_cast<float*>(ws + l.off_wtab));
     const long long npx = (long long)B * H * W;
     SSLB_DISPATCH_DTYPE(dtype, T, {
         auto k = ssg_plane_bwd_kernel<T, Cfg>;
         SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<dim3(l.n_btiles, Cfg::NDXG), Cfg::THREADS, smem, st>>>(bp);
+        {
+            StageTimer timer(kStagePlaneBwd, st);
+            k<<<dim3(l.n_btiles, Cfg::NDXG), Cfg::THREADS, smem, st>>>(bp);
+        }
+        StageTimer timer(kStageFinish, st);
+        plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(rp.gcls, lists.counts, l.cap,
+                                                               reinterpret_cast<float*>(ws + l.off_wtab));
         plane_finish_kernel<T, Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
     });
     return check_launch("plane_backward", 4);

@@ -41,6 +41,7 @@ int launch_point_forward(PointParams& p, int dtype, int n_images, cudaStream_t s
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
     if (p.max_edges <= 0) return 0;
+    StageTimer timer(kStagePointFwd, st);
     const bool tiled = p.ks == 25 && p.kw == 9;
     if (tiled) {
         constexpr int PITCH = 57;
@@ -68,6 +69,7 @@ int launch_point_backward(PointParams& p, int dtype, cudaStream_t st) {
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
     if (p.max_edges <= 0) return 0;
+    StageTimer timer(kStagePointBwd, st);
     const int TP = p.ks + 2 * (p.kw / 2);
     const size_t smem = (size_t)(p.C + 1) * TP * (TP | 1) * sizeof(float);
     const int blocks = min(p.max_edges, di.sm_count * 4);
@@ -141,6 +143,7 @@ extern "C" int ssl_b200_build_edge_list(const float* mask, int B, int mask_chann
     p.n_chunks = (int)((n_pixels + kElChunk - 1) / kElChunk);
     p.chunk_counts = static_cast<int32_t*>(workspace);
     p.chunk_offsets = p.chunk_counts + p.n_chunks;
+    StageTimer timer(kStageEdgeList, st);
     SSLB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (2 + B), st));
     edge_count_kernel<<<p.n_chunks, kElThreads, 0, st>>>(p);
     edge_scan_kernel<<<1, 1024, 0, st>>>(p);
@@ -223,6 +226,7 @@ extern "C" int ssl_b200_row_loss(const float* rows_sr, const float* rows_gt, con
     p.mode = rows_mode; p.w_l1 = w_l1; p.w_kl = w_kl; p.scratch = scratch;
     const int blocks = min(max_edges, ssl_b200_row_loss_blocks());
     cudaStream_t st = (cudaStream_t)stream;
+    StageTimer timer(kStageRowLoss, st);
     row_loss_kernel<<<blocks, kRowThreads, 0, st>>>(p);
     row_loss_finalize_kernel<<<1, 32, 0, st>>>(scratch, blocks, sums);
     return check_launch("row_loss", 2);
@@ -522,6 +526,31 @@ extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_hos
     }
     SSLB_CUDA(cudaStreamSynchronize(st));
     if (n_rows_host) *n_rows_host = n_rows;
+    return 0;
+}
+
+extern "C" int ssl_b200_profile_enable(int on) {
+    Profiler& p = profiler();
+    p.enabled = on != 0;
+    p.n = 0;
+    return 0;
+}
+
+extern "C" int ssl_b200_profile_num_stages(void) { return kNumStages; }
+extern "C" const char* ssl_b200_profile_stage_name(int i) { return stage_name(i); }
+
+extern "C" int ssl_b200_profile_read(float* ms, int* launches) {
+    SSLB_REQUIRE(ms && launches, "null pointer");
+    Profiler& p = profiler();
+    for (int i = 0; i < kNumStages; ++i) { ms[i] = 0.f; launches[i] = 0; }
+    for (int i = 0; i < p.n; ++i) {
+        SSLB_CUDA(cudaEventSynchronize(p.stop[i]));
+        float t = 0.f;
+        SSLB_CUDA(cudaEventElapsedTime(&t, p.start[i], p.stop[i]));
+        ms[p.stage[i]] += t;
+        launches[p.stage[i]] += 1;
+    }
+    p.n = 0;
     return 0;
 }
 
