@@ -28,7 +28,8 @@ struct PlaneBwdCfg {
     static constexpr int TXB = Cfg::TXF;                 // same sweep geometry as the forward
     static constexpr int NCHB = TXB / 8 + 1;
     static constexpr int ACC_PITCH = TXB + 4;            // 4 * odd
-    static constexpr int U_PLANE = Cfg::ROWS * 8;        // swizzled [row][8]
+    static constexpr int U_COL = Cfg::ROWS + 4;          // one u column: 64 rows + the slot the last "-val" lands in
+    static constexpr int U_PLANE = 8 * U_COL;            // [8 columns][U_COL]
     static constexpr int U_WORKER = G * U_PLANE;
     // edge-pixel region a tile needs: rows [Yb0-P, Yb0+64+P), columns [Xb0-P-8, Xb0+TXB+P)
     static constexpr int RROWS = Cfg::ROWS + 2 * P;
@@ -92,19 +93,23 @@ __global__ void __launch_bounds__(256) plane_bwd_lists_kernel(PlaneBwdParams p, 
     }
 }
 
-// swizzled u plane: element (row, col) of a [64][8] plane; float4 reads of a row are conflict-free
-__device__ __forceinline__ int u_index(int row, int col) { return row * 8 + (col ^ (((row >> 2) & 1) << 2)); }
-
-// Place the items of one (plane j, u-column c8) of chunk k: v-direction applied while placing.
+// Build one column of one sparse plane: the thread owns u[column][0..63].
+// Every edge pixel that lands in this column covers a run of rows [r0, r1] (the v-direction of the
+// box); it is entered as +val at r0 and -val at r1+1 and the column is then prefix-summed in place,
+// so the cost per edge pixel is two shared-memory updates instead of up to 2K+1.
 template <typename Cfg>
 __device__ __forceinline__ void place_column(const PlaneBwdParams& p, const int32_t* cols, const int32_t* ent,
-                                             float* uplane, int c8, int xu, int dy, int dx) {
+                                             float* ucol, int xu, int dy, int dx) {
     using BC = PlaneBwdCfg<Cfg>;
     constexpr int P = Cfg::P, K = Cfg::K;
     const int alo = rng_lo(dy, P, K), ahi = rng_hi(dy, P, K);
     const int blo = rng_lo(dx, P, K), bhi = rng_hi(dx, P, K);
     const long long row1 = (long long)((dy + P) * Cfg::KS + dx + P) * p.cap;
     const long long row2 = (long long)((-dy + P) * Cfg::KS + (-dx) + P) * p.cap;
+    float4* ucol4 = reinterpret_cast<float4*>(ucol);
+#pragma unroll
+    for (int i = 0; i < BC::U_COL / 4; ++i) ucol4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int n_items = 0;
 #pragma unroll
     for (int kind = 0; kind < 2; ++kind) {
         // region column holding the edge pixels that land in u-column xu
@@ -130,9 +135,21 @@ __device__ __forceinline__ void place_column(const PlaneBwdParams& p, const int3
                 int r0 = rr + lo_off, r1 = rr + hi_off;
                 r0 = r0 < 0 ? 0 : r0;
                 r1 = r1 > Cfg::ROWS - 1 ? Cfg::ROWS - 1 : r1;
-                for (int rl = r0; rl <= r1; ++rl) uplane[u_index(rl, c8)] += val[m];
+                if (r0 > r1) continue;
+                ucol[r0] += val[m];
+                ucol[r1 + 1] -= val[m];
+                ++n_items;
             }
         }
+    }
+    if (n_items == 0) return;  // column stays exactly zero
+    float run = 0.f;
+#pragma unroll
+    for (int i = 0; i < Cfg::ROWS / 4; ++i) {
+        float4 v = ucol4[i];
+        v.x += run; v.y += v.x; v.z += v.y; v.w += v.z;
+        run = v.w;
+        ucol4[i] = v;
     }
 }
 
@@ -147,12 +164,11 @@ __device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* 
     for (int j = 0; j < GJ; ++j) {
         const int dx = GC::DX0 + j;
         const int len = rng_hi(dx, P, K) - rng_lo(dx, P, K) + 1;
-        const float* up = uworker + j * PlaneBwdCfg<Cfg>::U_PLANE + r * 8;
-        const int sw = ((r >> 2) & 1) << 2;
+        const float* up = uworker + j * PlaneBwdCfg<Cfg>::U_PLANE + r;
         float w[16], s2[16], s4[16], s8[16];
-        float4 a = *reinterpret_cast<const float4*>(up + (0 ^ sw));
-        float4 b = *reinterpret_cast<const float4*>(up + (4 ^ sw));
-        const float cur[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float cur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = up[i * PlaneBwdCfg<Cfg>::U_COL];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { w[i] = wprev[j][i]; w[8 + i] = cur[i]; wprev[j][i] = cur[i]; }
 #pragma unroll
@@ -225,14 +241,12 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
 #pragma unroll
                     for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
             }
-            // 1. clear this worker's u planes
-            for (int i = r; i < GJ * BC::U_PLANE / 4; i += Cfg::ROWS)
-                reinterpret_cast<float4*>(uworker)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // 1. build the chunk's 8 u-columns of every plane (one thread per column; it also clears it;
+            //    the CTA barrier that ended the previous phase ordered the previous sweep's reads before this)
+            if (pj < GJ)
+                place_column<Cfg>(p, cols, ent, uworker + pj * BC::U_PLANE + c8 * BC::U_COL, 8 * k + c8, dy, GC::DX0 + pj);
             worker_sync(wp);
-            // 2. place the items of the chunk's 8 u-columns
-            if (pj < GJ) place_column<Cfg>(p, cols, ent, uworker + pj * BC::U_PLANE, c8, 8 * k + c8, dy, GC::DX0 + pj);
-            worker_sync(wp);
-            // 3. h-direction + products, 4. add into the accumulator tile (output chunk k-1)
+            // 2. h-direction + products, 3. add into the accumulator tile (output chunk k-1)
             float acc[3][8];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
