@@ -12,9 +12,8 @@
 // the NumPy statement of these placement rules.
 //
 // One CTA = one 64 x TXB tile of the PADDED image and one dx-group; its NWP workers (warp pairs,
-// lane = image row) take dy = w, w+NWP, ...  Workers run the same (dy, chunk) sequence skewed by one
-// phase each, so that at any time they add into different 8-column chunks of the shared
-// accumulator tile; a CTA barrier ends each phase (deterministic order, no atomics).
+// lane = image row) take dy = w, w+NWP, ... and free-run; additions into the shared accumulator tile
+// are ordered by per-chunk tickets (deterministic summation order, no atomics).
 #pragma once
 
 #include "plane_geom.cuh"
@@ -215,45 +214,47 @@ __device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* 
     }
 }
 
+// Workers free-run through their own (dy, chunk) sequence.  The only shared state is the accumulator
+// tile; additions into its 8-column chunk c are serialised by a ticket per chunk, handed out in the
+// fixed order (dy-round, worker), so the summation order -- and the result -- is the same every run.
 template <typename Cfg, int GI>
 __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const float* tile, float* ubuf, float* accT,
-                                              const int32_t* cols, const int32_t* ent) {
+                                              const int32_t* cols, const int32_t* ent, volatile int* turn) {
     using GC = GroupConsts<Cfg, GI>;
     using BC = PlaneBwdCfg<Cfg>;
     constexpr int P = Cfg::P, GJ = GC::GJ, NWP = Cfg::NWP;
     const int tid = threadIdx.x;
     const int wp = tid / Cfg::ROWS, r = tid % Cfg::ROWS;
     float* uworker = ubuf + wp * BC::U_WORKER;
-    constexpr int NDY_MAX = (Cfg::KS + NWP - 1) / NWP;
-    const int n_seq = NDY_MAX * BC::NCHB;
     // place-side role: (u-column c8, plane pj)
     const int c8 = r & 7, pj = r >> 3;
     float wprev[GJ][8];
-    for (int phase = 0; phase < n_seq + NWP - 1; ++phase) {
-        const int n = phase - wp;
-        const int idy = n / BC::NCHB, k = n - idy * BC::NCHB;
-        const int dy = wp - P + idy * NWP;
-        const bool active = n >= 0 && n < n_seq && dy <= P;
-        if (active) {
-            if (k == 0) {
+    int idy = 0;
+    for (int dy = wp - P; dy <= P; dy += NWP, ++idy) {
 #pragma unroll
-                for (int j = 0; j < GJ; ++j)
+        for (int j = 0; j < GJ; ++j)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
-            }
-            // 1. build the chunk's 8 u-columns of every plane (one thread per column; it also clears it;
-            //    the CTA barrier that ended the previous phase ordered the previous sweep's reads before this)
+            for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
+        const int ticket = idy * NWP + wp;
+        for (int k = 0; k < BC::NCHB; ++k) {
+            worker_sync(wp);  // the previous chunk's sweep has finished reading u
+            // 1. build the chunk's 8 u-columns of every plane (one thread per column; it also clears it)
             if (pj < GJ)
                 place_column<Cfg>(p, cols, ent, uworker + pj * BC::U_PLANE + c8 * BC::U_COL, 8 * k + c8, dy, GC::DX0 + pj);
             worker_sync(wp);
-            // 2. h-direction + products, 3. add into the accumulator tile (output chunk k-1)
+            // 2. h-direction + products
             float acc[3][8];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
             sweep_chunk_bwd<Cfg, GI>(tile, uworker, r, dy, k, wprev, acc);
+            // 3. add into the accumulator tile (output chunk k-1) when it is this worker's turn
             if (k >= 1) {
+                if (r == 0)
+                    while (turn[k - 1] != ticket) __nanosleep(32);
+                worker_sync(wp);
+                __threadfence_block();
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float4* dst = reinterpret_cast<float4*>(accT + (c * Cfg::ROWS + r) * BC::ACC_PITCH + 8 * (k - 1));
@@ -262,9 +263,11 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
                     v1.x += acc[c][4]; v1.y += acc[c][5]; v1.z += acc[c][6]; v1.w += acc[c][7];
                     dst[0] = v0; dst[1] = v1;
                 }
+                __threadfence_block();
+                worker_sync(wp);
+                if (r == 0) turn[k - 1] = ticket + 1;
             }
         }
-        __syncthreads();
     }
 }
 
@@ -277,6 +280,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(PlaneBwd
     float* accT = ubuf + Cfg::NWP * BC::U_WORKER;
     int32_t* ent_s = reinterpret_cast<int32_t*>(accT + 3 * Cfg::ROWS * BC::ACC_PITCH);
     __shared__ int32_t cols_s[BC::RCOLS + 1];
+    __shared__ int turn_s[BC::NCHB];
+    if (threadIdx.x < BC::NCHB) turn_s[threadIdx.x] = 0;
     const int t = blockIdx.x;
     const int txb = t % p.ntxb, tyb = (t / p.ntxb) % p.ntyb, b = t / (p.ntxb * p.ntyb);
     const int32_t* cols_g = p.tile_cols + (long long)t * (BC::RCOLS + 1);
@@ -301,13 +306,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(PlaneBwd
     const int32_t* ent = staged ? ent_s : ent_g;
     __syncthreads();
     switch (blockIdx.y) {
-        case 0: run_group_bwd<Cfg, 0>(p, tile, ubuf, accT, cols_s, ent); break;
-        case 1: if constexpr (Cfg::NDXG > 1) run_group_bwd<Cfg, 1>(p, tile, ubuf, accT, cols_s, ent); break;
-        case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, ent); break;
-        case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, ent); break;
-        case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, ent); break;
+        case 0: run_group_bwd<Cfg, 0>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
+        case 1: if constexpr (Cfg::NDXG > 1) run_group_bwd<Cfg, 1>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
+        case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
+        case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
+        case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
         default: break;
     }
+    __syncthreads();
     // the factor 2 of d(t^2) is applied here, once
     for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::TXB; i += blockDim.x) {
         const int xo = i % BC::TXB, rr = (i / BC::TXB) % Cfg::ROWS, c = i / (BC::TXB * Cfg::ROWS);
