@@ -120,7 +120,7 @@ struct PlaneStepLayout {
     PlaneGeom g;
     int cap;
     PlaneListsLayout lists;
-    size_t off_q[2], off_eout[2], off_gcls, off_wtab, off_scratch, off_tcols, off_tent, off_gpart, total;
+    size_t off_q[2], off_eout[2], off_gcls, off_wtab, off_scratch, off_tcols, off_tent, off_gpart, off_wsum, total;
     int ntyb, ntxb, HT, WT, n_btiles, loss_blocks;
 };
 
@@ -145,11 +145,12 @@ inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int
     l.off_gcls = o; o += align256((size_t)l.cap * nc2 * sizeof(float));
     l.off_wtab = o; o += align256((size_t)l.cap * Cfg::KW * Cfg::KW * sizeof(float));
     l.off_scratch = o; o += align256((size_t)2 * loss_blocks * sizeof(double));
-    l.off_tcols = o; l.off_tent = o; l.off_gpart = o;
+    l.off_tcols = o; l.off_tent = o; l.off_gpart = o; l.off_wsum = o;
     if (want_grad) {
         o += align256((size_t)l.n_btiles * (BC::RCOLS + 1) * sizeof(int32_t));
         l.off_tent = o; o += align256((size_t)l.n_btiles * BC::LIST_STRIDE * sizeof(int32_t));
         l.off_gpart = o; o += align256((size_t)Cfg::NDXG * B * 3 * l.HT * l.WT * sizeof(float));
+        l.off_wsum = o; o += align256((size_t)B * l.HT * l.WT * sizeof(float));
     }
     l.total = o;
     return l;
@@ -163,7 +164,7 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
     using BC = PlaneBwdCfg<Cfg>;
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
-    const int loss_blocks = di.sm_count;
+    const int loss_blocks = 2 * di.sm_count;
     const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, loss_blocks, grad_sr != nullptr);
     SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
     char* ws = static_cast<char*>(workspace);
@@ -183,7 +184,7 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
     rp.mode = rows_mode; rp.want_grad = grad_sr ? 1 : 0; rp.w_l1 = w_l1; rp.w_kl = w_kl;
     rp.gcls = grad_sr ? reinterpret_cast<float*>(ws + l.off_gcls) : nullptr;
     rp.scratch = reinterpret_cast<double*>(ws + l.off_scratch);
-    const size_t rl_smem = (size_t)2 * Cfg::L * 32 * sizeof(float);
+    const size_t rl_smem = (size_t)2 * Cfg::L * kRowTSlots * sizeof(float);
     SSLB_CUDA(cudaFuncSetAttribute(row_loss_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl_smem));
     {
         StageTimer timer(kStageRowLoss, st);
@@ -210,6 +211,7 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
     PlaneFinishParams fp{};
     fp.img = sr; fp.gpart = bp.gpart; fp.wtab = reinterpret_cast<float*>(ws + l.off_wtab);
     fp.slot_map = lists.slot_map; fp.grad = grad_sr;
+    fp.wsum = reinterpret_cast<float*>(ws + l.off_wsum);
     fp.B = B; fp.H = H; fp.W = W; fp.HT = l.HT; fp.WT = l.WT; fp.n_parts = Cfg::NDXG; fp.cap = l.cap;
     const long long npx = (long long)B * H * W;
     SSLB_DISPATCH_DTYPE(dtype, T, {
@@ -222,9 +224,10 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
         StageTimer timer(kStageFinish, st);
         plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(rp.gcls, lists.counts, l.cap,
                                                                reinterpret_cast<float*>(ws + l.off_wtab));
+        plane_wsum_kernel<Cfg><<<dim3(l.WT / 16, l.HT / 16, B), 256, 0, st>>>(fp);
         plane_finish_kernel<T, Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
     });
-    return check_launch("plane_backward", 4);
+    return check_launch("plane_backward", 5);
 }
 
 }  // namespace sslb

@@ -1,7 +1,7 @@
 // Row loss on the offset-major rows of the plane path: qT[d][slot].
 //
-// One block owns 32 consecutive slots and keeps both of their rows (SR and GT, KS*KS entries each)
-// in shared memory, so the exp / normalise tail of loss_util.py:234-243, the L1 (basic_loss.py:
+// One block owns 16 consecutive slots and keeps both of their rows (SR and GT, KS*KS entries each)
+// in shared memory (80 KB: two blocks per SM overlap one block's loads with the other's arithmetic), so the exp / normalise tail of loss_util.py:234-243, the L1 (basic_loss.py:
 // 14-16,59-66) and KL (basic_loss.py:269-282) numerators and the whole adjoint chain down to
 // dL/dq cost one read of each rows buffer and one write (dL/dq overwrites q_sr in place).
 // It also emits, per slot, the sum of dL/dq over every clip class: the weights of the
@@ -27,18 +27,20 @@ struct RowLossTParams {
 };
 
 constexpr int kRowTThreads = 512;
-constexpr int kRowTPhases = kRowTThreads / 32;
+constexpr int kRowTSlots = 16;                       // slots per block: 2 rows x 625 x 16 floats = 80 KB => 2 blocks per SM
+constexpr int kRowTPhases = kRowTThreads / kRowTSlots;
 
 __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams p) {
     extern __shared__ float rl_smem[];
-    float* es = rl_smem;                // [L][32]
-    float* et = es + p.L * 32;          // [L][32]
-    __shared__ float red[2][kRowTPhases][32];
+    constexpr int NS = kRowTSlots;
+    float* es = rl_smem;                // [L][NS]
+    float* et = es + p.L * NS;          // [L][NS]
+    __shared__ float red[2][kRowTPhases][NS];
     __shared__ double dred[32];
-    const int s = threadIdx.x & 31, ph = threadIdx.x >> 5;
+    const int s = threadIdx.x % NS, ph = threadIdx.x / NS;
     const int n_slots = min(p.counts[0], p.cap);
     double l1_tot = 0.0, kl_tot = 0.0;
-    for (int slot0 = blockIdx.x * 32; slot0 < n_slots; slot0 += gridDim.x * 32) {
+    for (int slot0 = blockIdx.x * NS; slot0 < n_slots; slot0 += gridDim.x * NS) {
         const int slot = slot0 + s;
         const bool valid = slot < n_slots && p.slot_pix[slot] >= 0;
         // pass 1: e = exp(-1 * (q / (C kw^2)) / sigma), partial row sums.  Loads are issued in batches
@@ -60,8 +62,8 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
                 if (d < p.L) {
                     const float a = valid ? expf(-1.0f * (qa[u] / p.denom) / p.sigma) : 0.f;
                     const float b = valid ? expf(-1.0f * (qb[u] / p.denom) / p.sigma) : 0.f;
-                    es[d * 32 + s] = a;
-                    et[d * 32 + s] = b;
+                    es[d * NS + s] = a;
+                    et[d * NS + s] = b;
                     zs += a;
                     zt += b;
                 }
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
         // pass 2: rows, loss terms, dL/drow; es <- s, et <- g
         float l1 = 0.f, kl = 0.f, dot = 0.f;
         for (int d = ph; d < p.L; d += kRowTPhases) {
-            const float sv = rs * es[d * 32 + s], tv = rt * et[d * 32 + s];
+            const float sv = rs * es[d * NS + s], tv = rt * et[d * NS + s];
             const float df = sv - tv;
             l1 += fabsf(df);
             float g = p.w_l1 * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
@@ -93,8 +95,8 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
             }
             if (!valid) g = 0.f;
             dot = fmaf(g, sv, dot);
-            es[d * 32 + s] = sv;
-            et[d * 32 + s] = g;
+            es[d * NS + s] = sv;
+            et[d * NS + s] = g;
         }
         if (valid) { l1_tot += (double)l1; kl_tot += (double)kl; }
         if (p.want_grad) {
@@ -107,8 +109,8 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
             }
             // pass 3: dL/dq = chain * s * (g - sum_m g_m s_m)   (EXP rows: chain * e * g)
             for (int d = ph; d < p.L; d += kRowTPhases) {
-                const float gq = p.chain * es[d * 32 + s] * (et[d * 32 + s] - dsum);
-                es[d * 32 + s] = gq;
+                const float gq = p.chain * es[d * NS + s] * (et[d * NS + s] - dsum);
+                es[d * NS + s] = gq;
                 if (slot < n_slots) p.qs[(long long)d * p.cap + slot] = gq;
             }
             __syncthreads();
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
                         const int dx0 = cb < p.K ? cb - p.P : (cb > p.K ? U + (cb - p.K) : -U);
                         const int dx1 = cb == p.K ? U : dx0;
                         for (int dy = dy0; dy <= dy1; ++dy)
-                            for (int dx = dx0; dx <= dx1; ++dx) acc += es[((dy + p.P) * p.KS + dx + p.P) * 32 + s];
+                            for (int dx = dx0; dx <= dx1; ++dx) acc += es[((dy + p.P) * p.KS + dx + p.P) * NS + s];
                     }
                     p.gcls[(long long)c * p.cap + slot] = acc;
                 }

@@ -368,14 +368,47 @@ struct PlaneFinishParams {
     const float* gpart;       // [NDXG][B][3][HT][WT]
     const float* wtab;        // [cap][KW*KW]
     const int32_t* slot_map;
+    float* wsum;              // [B][HT][WT] out-of-area weight of every padded pixel
     float* grad;              // [B,3,H,W], overwritten
     int B, H, W, HT, WT, n_parts, cap;
 };
 
+// wsum(Y,X) = sum over the edge pixels p = (Y,X) - (a,b), |a|,|b| <= K, of wtab[p][(a,b)].
+// One block = 16x16 padded pixels; the slots of the (16+2K)^2 pixels around it are staged once.
+template <typename Cfg>
+__global__ void __launch_bounds__(256) plane_wsum_kernel(PlaneFinishParams p) {
+    constexpr int P = Cfg::P, K = Cfg::K, KW = Cfg::KW, T = 16, R = T + 2 * K;
+    __shared__ int32_t ss[R][R + 1];
+    const int b = blockIdx.z, Y0 = blockIdx.y * T, X0 = blockIdx.x * T;
+    int any = 0;
+    for (int i = threadIdx.x; i < R * R; i += 256) {
+        const int ry = i / R, rx = i % R;
+        const int y = Y0 + ry - K - P, x = X0 + rx - K - P;   // image coordinates of padded (Y0+ry-K, X0+rx-K)
+        int slot = -1;
+        if (y >= 0 && y < p.H && x >= 0 && x < p.W) slot = p.slot_map[(b * p.H + y) * p.W + x];
+        if (slot >= p.cap) slot = -1;
+        ss[ry][rx] = slot;
+        any |= slot >= 0;
+    }
+    any = __syncthreads_or(any);
+    const int ty = threadIdx.x / T, tx = threadIdx.x % T;
+    float w = 0.f;
+    if (any) {
+        // edge pixel at region (ty + K - a, tx + K - b) reaches this pixel with window offset (a, b)
+        for (int a = -K; a <= K; ++a)
+#pragma unroll
+            for (int bb = -K; bb <= K; ++bb) {
+                const int slot = ss[ty + K - a][tx + K - bb];
+                if (slot >= 0) w += p.wtab[(long long)slot * (KW * KW) + (a + K) * KW + bb + K];
+            }
+    }
+    p.wsum[((long long)b * p.HT + Y0 + ty) * p.WT + X0 + tx] = w;
+}
+
 // Padded-domain gradient at (Y,X) of image b, all three channels.
 template <typename T, typename Cfg>
 __device__ __forceinline__ void padded_grad_at(const PlaneFinishParams& p, const T* img, int b, int Y, int X, float (&g)[3]) {
-    constexpr int P = Cfg::P, K = Cfg::K, KW = Cfg::KW;
+    constexpr int P = Cfg::P;
     const long long plane = (long long)p.HT * p.WT;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -384,18 +417,7 @@ __device__ __forceinline__ void padded_grad_at(const PlaneFinishParams& p, const
             s += p.gpart[(((long long)part * p.B + b) * 3 + c) * plane + (long long)Y * p.WT + X];
         g[c] = s;
     }
-    // out-of-area weight: every edge pixel p = x - (a,b) within the window reach
-    float wsum = 0.f;
-    for (int a = -K; a <= K; ++a) {
-        const int y = Y - a - P;
-        if (y < 0 || y >= p.H) continue;
-        for (int bb = -K; bb <= K; ++bb) {
-            const int x = X - bb - P;
-            if (x < 0 || x >= p.W) continue;
-            const int slot = p.slot_map[(b * p.H + y) * p.W + x];
-            if (slot >= 0 && slot < p.cap) wsum += p.wtab[(long long)slot * (KW * KW) + (a + K) * KW + bb + K];
-        }
-    }
+    const float wsum = p.wsum[(long long)b * plane + (long long)Y * p.WT + X];
     const int sy = reflect_idx(Y - P, p.H), sx = reflect_idx(X - P, p.W);
 #pragma unroll
     for (int c = 0; c < 3; ++c)

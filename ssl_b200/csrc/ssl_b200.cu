@@ -361,7 +361,7 @@ extern "C" size_t ssl_b200_loss_workspace_bytes(int B, int C, int H, int W, int 
     if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
     if (!use_plane_path(path, B, C, H, W, ks, kw, max_edges)) return point_loss_workspace_bytes(ks, max_edges);
     DeviceInfo di;
-    const int loss_blocks = device_info(&di) ? 148 : di.sm_count;
+    const int loss_blocks = 2 * (device_info(&di) ? 148 : di.sm_count);
     SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, { return plane_step_layout<Cfg>(B, H, W, max_edges, loss_blocks, true).total; });
 }
 
