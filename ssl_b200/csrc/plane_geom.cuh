@@ -17,17 +17,19 @@
 namespace sslb {
 
 // Compile-time geometry of one (k_search, k_window) configuration.
-template <int KS_, int KW_>
+// ROWS = image rows one worker covers (its threads), G = consecutive dx per sweep thread, NWP = workers
+// per CTA (worker w takes dy = w, w+NWP, ...).  The forward uses (64, 5, 5): it needs a halo of K rows
+// on each side, so tall workers waste less; the backward has no row halo and uses (32, 4, 13).
+template <int KS_, int KW_, int ROWS_ = 64, int G_ = 5, int NWP_ = 5>
 struct PlaneCfg {
     static constexpr int KS = KS_, KW = KW_;
     static constexpr int P = KS / 2, K = KW / 2;
     static constexpr int L = KS * KS;
-    static constexpr int G = 5;            // consecutive dx handled by one sweep thread
-    static constexpr int NWP = 5;          // warp pairs per CTA = consecutive dy per step
-    static constexpr int NPL = G * NWP;    // planes resident per step (<= 32: one lane each)
+    static constexpr int G = G_;           // consecutive dx handled by one sweep thread
+    static constexpr int NWP = NWP_;       // workers per CTA
+    static constexpr int NPL = G * NWP;    // box-summed planes resident per CTA
     static constexpr int NDXG = (KS + G - 1) / G;
-    static constexpr int NDYS = (KS + NWP - 1) / NWP;
-    static constexpr int ROWS = 64;        // lanes of a warp pair = image rows of a tile incl. halo
+    static constexpr int ROWS = ROWS_;     // threads of a worker = image rows it covers (incl. halo in the forward)
     static constexpr int THREADS = NWP * ROWS;
     static constexpr int NCLS = 2 * K + 1; // clip classes per axis
     // forward tiles (unpadded image coordinates of the edge pixels they own)
@@ -48,9 +50,13 @@ struct PlaneCfg {
     static constexpr int SPS = (ROWS * SRP) | 1;         // odd plane stride
     static constexpr int RC_SMEM = 2048;                 // slot descriptors of a tile staged in shared memory
     static_assert(KS % 2 == 1 && KW % 2 == 1 && KW <= KS && KW <= 9, "unsupported kernel sizes");
-    static_assert(NPL <= 32, "one lane per plane");
+    static_assert(ROWS == 32 || ROWS == 64, "a worker is one warp or a warp pair");
     static_assert(2 * K <= CH, "gather lags the sweep by one chunk");
 };
+
+// Backward geometry that goes with a forward configuration.
+template <typename Cfg>
+using PlaneBwdGeom = PlaneCfg<Cfg::KS, Cfg::KW, 32, 4, 13>;
 
 // in-area range of window offsets for search offset t, per axis
 __host__ __device__ constexpr int rng_lo(int t, int P, int K) { return -P - t > -K ? -P - t : -K; }

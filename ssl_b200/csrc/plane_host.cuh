@@ -126,16 +126,17 @@ struct PlaneStepLayout {
 
 template <typename Cfg>
 inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int loss_blocks, bool want_grad) {
-    using BC = PlaneBwdCfg<Cfg>;
+    using BG = PlaneBwdGeom<Cfg>;
+    using BC = PlaneBwdCfg<BG>;
     PlaneStepLayout l;
     l.g = geom_for<Cfg>(B, H, W);
     l.cap = slot_capacity(max_edges, l.g.n_units);
     l.lists = plane_lists_layout(l.g, l.cap);
     l.loss_blocks = loss_blocks;
     const int Hp = H + 2 * Cfg::P, Wp = W + 2 * Cfg::P;
-    l.ntyb = (Hp + Cfg::ROWS - 1) / Cfg::ROWS;
+    l.ntyb = (Hp + BG::ROWS - 1) / BG::ROWS;
     l.ntxb = (Wp + BC::TXB - 1) / BC::TXB;
-    l.HT = l.ntyb * Cfg::ROWS;
+    l.HT = l.ntyb * BG::ROWS;
     l.WT = l.ntxb * BC::TXB;
     l.n_btiles = B * l.ntyb * l.ntxb;
     const size_t nc2 = (size_t)Cfg::NCLS * Cfg::NCLS;
@@ -149,7 +150,7 @@ inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int
     if (want_grad) {
         o += align256((size_t)l.n_btiles * (BC::RCOLS + 1) * sizeof(int32_t));
         l.off_tent = o; o += align256((size_t)l.n_btiles * BC::LIST_STRIDE * sizeof(int32_t));
-        l.off_gpart = o; o += align256((size_t)Cfg::NDXG * B * 3 * l.HT * l.WT * sizeof(float));
+        l.off_gpart = o; o += align256((size_t)BG::NDXG * B * 3 * l.HT * l.WT * sizeof(float));
         l.off_wsum = o; o += align256((size_t)B * l.HT * l.WT * sizeof(float));
     }
     l.total = o;
@@ -161,7 +162,8 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
                                  const int32_t* counts, int max_edges, float sigma, float eps, int rows_mode,
                                  float w_l1, float w_kl, float* grad_sr, double* terms, void* workspace,
                                  size_t workspace_bytes, cudaStream_t st) {
-    using BC = PlaneBwdCfg<Cfg>;
+    using BG = PlaneBwdGeom<Cfg>;
+    using BC = PlaneBwdCfg<BG>;
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
     const int loss_blocks = 2 * di.sm_count;
@@ -204,22 +206,22 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
     bp.ntyb = l.ntyb; bp.ntxb = l.ntxb; bp.HT = l.HT; bp.WT = l.WT;
     {
         StageTimer timer(kStagePlaneBwdLists, st);
-        plane_bwd_lists_kernel<Cfg><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tent);
+        plane_bwd_lists_kernel<BG><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tent);
     }
-    const size_t smem = plane_bwd_smem_bytes<Cfg>();
+    const size_t smem = plane_bwd_smem_bytes<BG>();
     SSLB_REQUIRE(smem <= (size_t)di.max_smem_optin, "plane backward needs %zu B of shared memory", smem);
     PlaneFinishParams fp{};
     fp.img = sr; fp.gpart = bp.gpart; fp.wtab = reinterpret_cast<float*>(ws + l.off_wtab);
     fp.slot_map = lists.slot_map; fp.grad = grad_sr;
     fp.wsum = reinterpret_cast<float*>(ws + l.off_wsum);
-    fp.B = B; fp.H = H; fp.W = W; fp.HT = l.HT; fp.WT = l.WT; fp.n_parts = Cfg::NDXG; fp.cap = l.cap;
+    fp.B = B; fp.H = H; fp.W = W; fp.HT = l.HT; fp.WT = l.WT; fp.n_parts = BG::NDXG; fp.cap = l.cap;
     const long long npx = (long long)B * H * W;
     SSLB_DISPATCH_DTYPE(dtype, T, {
-        auto k = ssg_plane_bwd_kernel<T, Cfg>;
+        auto k = ssg_plane_bwd_kernel<T, BG>;
         SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             StageTimer timer(kStagePlaneBwd, st);
-            k<<<dim3(l.n_btiles, Cfg::NDXG), Cfg::THREADS, smem, st>>>(bp);
+            k<<<dim3(l.n_btiles, BG::NDXG), BG::THREADS, smem, st>>>(bp);
         }
         StageTimer timer(kStageFinish, st);
         plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(rp.gcls, lists.counts, l.cap,

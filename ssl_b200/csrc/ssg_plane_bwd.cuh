@@ -27,7 +27,7 @@ struct PlaneBwdCfg {
     static constexpr int TXB = Cfg::TXF;                 // same sweep geometry as the forward
     static constexpr int NCHB = TXB / 8 + 1;
     static constexpr int ACC_PITCH = TXB + 4;            // 4 * odd
-    static constexpr int U_COL = Cfg::ROWS + 4;          // one u column: 64 rows + the slot the last "-val" lands in
+    static constexpr int U_COL = Cfg::ROWS + 4;          // one u column: ROWS rows + the slot the last "-val" lands in
     static constexpr int U_PLANE = 8 * U_COL;            // [8 columns][U_COL]
     static constexpr int U_WORKER = G * U_PLANE;
     // edge-pixel region a tile needs: rows [Yb0-P, Yb0+64+P), columns [Xb0-P-8, Xb0+TXB+P)
@@ -36,6 +36,8 @@ struct PlaneBwdCfg {
     static constexpr int LIST_STRIDE = RROWS * RCOLS;    // worst case entries per tile
     static constexpr int LIST_SMEM = 2560;               // entries staged in shared memory
     static_assert((ACC_PITCH / 4) % 2 == 1, "accumulator rows must be float4 conflict-free");
+    static_assert(G * 8 <= Cfg::ROWS, "one thread per (plane, u-column) when placing");
+    static_assert(Cfg::NDXG <= 7, "dx-group dispatch");
 };
 
 struct PlaneBwdParams {
@@ -237,11 +239,11 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
             for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
         const int ticket = idy * NWP + wp;
         for (int k = 0; k < BC::NCHB; ++k) {
-            worker_sync(wp);  // the previous chunk's sweep has finished reading u
+            worker_sync<Cfg::ROWS>(wp);  // the previous chunk's sweep has finished reading u
             // 1. build the chunk's 8 u-columns of every plane (one thread per column; it also clears it)
             if (pj < GJ)
                 place_column<Cfg>(p, cols, ent, uworker + pj * BC::U_PLANE + c8 * BC::U_COL, 8 * k + c8, dy, GC::DX0 + pj);
-            worker_sync(wp);
+            worker_sync<Cfg::ROWS>(wp);
             // 2. h-direction + products
             float acc[3][8];
 #pragma unroll
@@ -253,7 +255,7 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
             if (k >= 1) {
                 if (r == 0)
                     while (turn[k - 1] != ticket) __nanosleep(32);
-                worker_sync(wp);
+                worker_sync<Cfg::ROWS>(wp);
                 __threadfence_block();
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -264,7 +266,7 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
                     dst[0] = v0; dst[1] = v1;
                 }
                 __threadfence_block();
-                worker_sync(wp);
+                worker_sync<Cfg::ROWS>(wp);
                 if (r == 0) turn[k - 1] = ticket + 1;
             }
         }
@@ -311,6 +313,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(PlaneBwd
         case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
         case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
         case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
+        case 5: if constexpr (Cfg::NDXG > 5) run_group_bwd<Cfg, 5>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
+        case 6: if constexpr (Cfg::NDXG > 6) run_group_bwd<Cfg, 6>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
         default: break;
     }
     __syncthreads();

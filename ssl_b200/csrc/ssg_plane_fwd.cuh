@@ -201,8 +201,11 @@ __device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splane
     }
 }
 
+// Barrier among the threads of one worker: a named barrier for a warp pair, __syncwarp for one warp.
+template <int ROWS>
 __device__ __forceinline__ void worker_sync(int wp) {
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + wp) : "memory");
+    if (ROWS == 32) __syncwarp();
+    else asm volatile("bar.sync %0, 64;" ::"r"(1 + wp) : "memory");
 }
 
 // One worker = one warp pair = 64 image rows of one (dy, dx-group); workers of a CTA only share the
@@ -252,7 +255,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
                 for (int e = 0; e < 4; ++e) eo[e] = __ldg(eout + (long long)(gs_first + e) * (NC * NC) + cls);
             }
             sweep_chunk_fwd<Cfg, GI>(tile, splanes, r, dy, wp, k, wprev);
-            worker_sync(wp);
+            worker_sync<Cfg::ROWS>(wp);
             if (g_ok) {
                 for (int gs = gs_first; gs < s1; gs += 4 * NGRP) {
                     const int4 rc4 = *reinterpret_cast<const int4*>(slot_rc + (gs - slot0));
@@ -279,7 +282,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
                     *reinterpret_cast<float4*>(qT + qrow + gs) = make_float4(out[0], out[1], out[2], out[3]);
                 }
             }
-            worker_sync(wp);
+            worker_sync<Cfg::ROWS>(wp);
         }
     }
 }
