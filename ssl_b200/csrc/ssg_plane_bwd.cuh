@@ -157,47 +157,18 @@ __device__ __forceinline__ void place_column(const PlaneBwdParams& p, const int3
 // One chunk of the h-direction tree + products for one sweep thread.
 template <typename Cfg, int GI>
 __device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* uworker, int r, int dy, int k,
-                                                float (&wprev)[GroupConsts<Cfg, GI>::GJ][8], float (&acc)[3][8]) {
+                                                BoxCarry (&carry)[GroupConsts<Cfg, GI>::GJ], float (&acc)[3][8]) {
     using GC = GroupConsts<Cfg, GI>;
-    constexpr int P = Cfg::P, K = Cfg::K, GJ = GC::GJ, OFF = GC::OFF, NV4 = GC::NV4;
+    constexpr int P = Cfg::P, GJ = GC::GJ, OFF = GC::OFF, NV4 = GC::NV4;
     float gs[GJ][8];
-#pragma unroll
-    for (int j = 0; j < GJ; ++j) {
-        const int dx = GC::DX0 + j;
-        const int len = rng_hi(dx, P, K) - rng_lo(dx, P, K) + 1;
+    BoxDispatch<0, GJ>::template run<Cfg, GC::DX0>([&](auto jc, auto lenc) {
+        constexpr int j = decltype(jc)::value, len = decltype(lenc)::value;
         const float* up = uworker + j * PlaneBwdCfg<Cfg>::U_PLANE + r;
-        float w[16], s2[16], s4[16], s8[16];
         float cur[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = up[i * PlaneBwdCfg<Cfg>::U_COL];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { w[i] = wprev[j][i]; w[8 + i] = cur[i]; wprev[j][i] = cur[i]; }
-#pragma unroll
-        for (int i = 1; i < 16; ++i) s2[i] = w[i] + w[i - 1];
-#pragma unroll
-        for (int i = 3; i < 16; ++i) s4[i] = s2[i] + s2[i - 2];
-#pragma unroll
-        for (int i = 7; i < 16; ++i) s8[i] = s4[i] + s4[i - 4];
-        s2[0] = s4[0] = s4[1] = s4[2] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) s8[i] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float s;
-            switch (len) {
-                case 1: s = sum_last<1>(w, s2, s4, s8, 8 + i); break;
-                case 2: s = sum_last<2>(w, s2, s4, s8, 8 + i); break;
-                case 3: s = sum_last<3>(w, s2, s4, s8, 8 + i); break;
-                case 4: s = sum_last<4>(w, s2, s4, s8, 8 + i); break;
-                case 5: s = sum_last<5>(w, s2, s4, s8, 8 + i); break;
-                case 6: s = sum_last<6>(w, s2, s4, s8, 8 + i); break;
-                case 7: s = sum_last<7>(w, s2, s4, s8, 8 + i); break;
-                case 8: s = sum_last<8>(w, s2, s4, s8, 8 + i); break;
-                default: s = sum_last<9>(w, s2, s4, s8, 8 + i); break;
-            }
-            gs[j][i] = s;
-        }
-    }
+        box_last<len>(cur, carry[j], gs[j]);
+    });
     if (k == 0) return;  // chunk 0 only primes the tree (its outputs lie left of the tile)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -230,13 +201,11 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
     float* uworker = ubuf + wp * BC::U_WORKER;
     // place-side role: (u-column c8, plane pj)
     const int c8 = r & 7, pj = r >> 3;
-    float wprev[GJ][8];
+    BoxCarry carry[GJ];
     int idy = 0;
     for (int dy = wp - P; dy <= P; dy += NWP, ++idy) {
 #pragma unroll
-        for (int j = 0; j < GJ; ++j)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
+        for (int j = 0; j < GJ; ++j) box_carry_reset(carry[j]);
         const int ticket = idy * NWP + wp;
         for (int k = 0; k < BC::NCHB; ++k) {
             worker_sync<Cfg::ROWS>(wp);  // the previous chunk's sweep has finished reading u
@@ -250,7 +219,7 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
-            sweep_chunk_bwd<Cfg, GI>(tile, uworker, r, dy, k, wprev, acc);
+            sweep_chunk_bwd<Cfg, GI>(tile, uworker, r, dy, k, carry, acc);
             // 3. add into the accumulator tile (output chunk k-1) when it is this worker's turn
             if (k >= 1) {
                 if (r == 0)

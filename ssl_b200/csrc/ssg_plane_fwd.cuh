@@ -14,6 +14,8 @@
 // the algebra is restated and checked against the oracle in tests/dense_model.py.
 #pragma once
 
+#include <type_traits>
+
 #include "plane_geom.cuh"
 
 namespace sslb {
@@ -126,6 +128,59 @@ __device__ __forceinline__ float sum_last(const float* w, const float* s2, const
     return s8[i - 1] + w[i];  // LEN == 9
 }
 
+// Box sums of one plane over one 8-column chunk: out[i] = sum of the last LEN values ending at column i.
+// The pairwise partial sums (pairs, quads, octets) that reach back into the previous chunk are carried
+// in registers, so a chunk costs 4 additions per output for LEN = 9; carries a clipped LEN never reads
+// are dead code.
+struct BoxCarry {
+    float w[8], s2[4], s4[4], s8;
+};
+
+__device__ __forceinline__ void box_carry_reset(BoxCarry& c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c.w[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c.s2[i] = c.s4[i] = 0.f;
+    c.s8 = 0.f;
+}
+
+template <int LEN>
+__device__ __forceinline__ void box_last(const float (&cur)[8], BoxCarry& c, float (&out)[8]) {
+    float w[16], s2[16], s4[16], s8[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { w[i] = c.w[i]; w[8 + i] = cur[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s2[4 + i] = c.s2[i]; s4[4 + i] = c.s4[i]; }
+    s8[7] = c.s8;
+#pragma unroll
+    for (int i = 8; i < 16; ++i) s2[i] = w[i] + w[i - 1];
+#pragma unroll
+    for (int i = 8; i < 16; ++i) s4[i] = s2[i] + s2[i - 2];
+#pragma unroll
+    for (int i = 8; i < 16; ++i) s8[i] = s4[i] + s4[i - 4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = sum_last<LEN>(w, s2, s4, s8, 8 + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c.w[i] = cur[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c.s2[i] = s2[12 + i]; c.s4[i] = s4[12 + i]; }
+    c.s8 = s8[15];
+}
+
+template <int J, int JEND>
+struct BoxDispatch {
+    // compile-time loop over the planes of a group so that LEN is a template argument
+    template <typename Cfg, int DX0, typename F>
+    static __device__ __forceinline__ void run(F&& f) {
+        if constexpr (J < JEND) {
+            constexpr int dx = DX0 + J;
+            constexpr int len = rng_hi(dx, Cfg::P, Cfg::K) - rng_lo(dx, Cfg::P, Cfg::K) + 1;
+            f(std::integral_constant<int, J>{}, std::integral_constant<int, len>{});
+            BoxDispatch<J + 1, JEND>::template run<Cfg, DX0>(f);
+        }
+    }
+};
+
 template <typename Cfg, int GI>
 struct GroupConsts {
     static constexpr int DX0 = -Cfg::P + GI * Cfg::G;
@@ -134,12 +189,12 @@ struct GroupConsts {
     static constexpr int NV4 = (OFF + 8 + GJ - 1 + 3) / 4;
 };
 
-// One chunk of one sweep thread: D, box sums, ring store.  wprev carries the previous chunk's D.
+// One chunk of one sweep thread: D, box sums, ring store.
 template <typename Cfg, int GI>
 __device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splanes, int r, int dy, int wp, int k,
-                                                float (&wprev)[GroupConsts<Cfg, GI>::GJ][8]) {
+                                                BoxCarry (&carry)[GroupConsts<Cfg, GI>::GJ]) {
     using GC = GroupConsts<Cfg, GI>;
-    constexpr int P = Cfg::P, K = Cfg::K, GJ = GC::GJ, OFF = GC::OFF, NV4 = GC::NV4;
+    constexpr int P = Cfg::P, GJ = GC::GJ, OFF = GC::OFF, NV4 = GC::NV4;
     float d[GJ][8];
 #pragma unroll
     for (int j = 0; j < GJ; ++j)
@@ -163,42 +218,15 @@ __device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splane
                 d[j][i] = fmaf(t, t, d[j][i]);
             }
     }
+    float* sp0 = splanes + (wp * Cfg::G) * Cfg::SPS + r * Cfg::SRP + (k & 1) * 8;
+    BoxDispatch<0, GJ>::template run<Cfg, GC::DX0>([&](auto jc, auto lenc) {
+        constexpr int j = decltype(jc)::value, len = decltype(lenc)::value;
+        float s[8];
+        box_last<len>(d[j], carry[j], s);
+        float* sp = sp0 + j * Cfg::SPS;
 #pragma unroll
-    for (int j = 0; j < GJ; ++j) {
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int dx = GC::DX0 + j;
-        const int len = rng_hi(dx, P, K) - rng_lo(dx, P, K) + 1;
-        float w[16], s2[16], s4[16], s8[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { w[i] = wprev[j][i]; w[8 + i] = d[j][i]; wprev[j][i] = d[j][i]; }
-#pragma unroll
-        for (int i = 1; i < 16; ++i) s2[i] = w[i] + w[i - 1];
-#pragma unroll
-        for (int i = 3; i < 16; ++i) s4[i] = s2[i] + s2[i - 2];
-#pragma unroll
-        for (int i = 7; i < 16; ++i) s8[i] = s4[i] + s4[i - 4];
-        s2[0] = s4[0] = s4[1] = s4[2] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) s8[i] = 0.f;
-        float* sp = splanes + (wp * Cfg::G + j) * Cfg::SPS + r * Cfg::SRP + (k & 1) * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float s;
-            switch (len) {  // len is a compile-time constant after unrolling over j
-                case 1: s = sum_last<1>(w, s2, s4, s8, 8 + i); break;
-                case 2: s = sum_last<2>(w, s2, s4, s8, 8 + i); break;
-                case 3: s = sum_last<3>(w, s2, s4, s8, 8 + i); break;
-                case 4: s = sum_last<4>(w, s2, s4, s8, 8 + i); break;
-                case 5: s = sum_last<5>(w, s2, s4, s8, 8 + i); break;
-                case 6: s = sum_last<6>(w, s2, s4, s8, 8 + i); break;
-                case 7: s = sum_last<7>(w, s2, s4, s8, 8 + i); break;
-                case 8: s = sum_last<8>(w, s2, s4, s8, 8 + i); break;
-                default: s = sum_last<9>(w, s2, s4, s8, 8 + i); break;
-            }
-            sp[i] = s;
-        }
-    }
+        for (int i = 0; i < 8; ++i) sp[i] = s[i];
+    });
 }
 
 // Barrier among the threads of one worker: a named barrier for a warp pair, __syncwarp for one warp.
@@ -237,11 +265,9 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
         const int cls = ca * NC + cb;
         const long long qrow = (long long)((dy + P) * Cfg::KS + g_dx + P) * cap;
 
-        float wprev[GJ][8];
+        BoxCarry carry[GJ];
 #pragma unroll
-        for (int j = 0; j < GJ; ++j)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) wprev[j][i] = 0.f;
+        for (int j = 0; j < GJ; ++j) box_carry_reset(carry[j]);
 
         for (int k = 0; k < Cfg::NCH; ++k) {
             // Out-of-area terms of the first slot group this thread will gather after the sweep:
@@ -254,7 +280,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
 #pragma unroll
                 for (int e = 0; e < 4; ++e) eo[e] = __ldg(eout + (long long)(gs_first + e) * (NC * NC) + cls);
             }
-            sweep_chunk_fwd<Cfg, GI>(tile, splanes, r, dy, wp, k, wprev);
+            sweep_chunk_fwd<Cfg, GI>(tile, splanes, r, dy, wp, k, carry);
             worker_sync<Cfg::ROWS>(wp);
             if (g_ok) {
                 for (int gs = gs_first; gs < s1; gs += 4 * NGRP) {
