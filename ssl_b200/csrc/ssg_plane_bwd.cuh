@@ -110,37 +110,49 @@ __device__ __forceinline__ void place_column(const PlaneBwdParams& p, const int3
     float4* ucol4 = reinterpret_cast<float4*>(ucol);
 #pragma unroll
     for (int i = 0; i < BC::U_COL / 4; ++i) ucol4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int n_items = 0;
+    // Both kinds are walked together, NB entries of each per round, so that up to 2*NB loads of dL/dq are
+    // in flight before the first one is consumed (the loads are what this phase waits for).
+    constexpr int NB = 6;
+    int e0[2], e1[2], lo_off[2], hi_off[2];
+    const float* gq[2];
 #pragma unroll
     for (int kind = 0; kind < 2; ++kind) {
         // region column holding the edge pixels that land in u-column xu
         const int pcol = kind == 0 ? xu - blo + P : xu + dx + bhi + P;
-        if (pcol < 0 || pcol >= BC::RCOLS) continue;
-        const int e0 = cols[pcol], e1 = cols[pcol + 1];
+        const bool ok = pcol >= 0 && pcol < BC::RCOLS;
+        e0[kind] = ok ? cols[pcol] : 0;
+        e1[kind] = ok ? cols[pcol + 1] : 0;
         // rows covered by an entry at region row rr: [rr + lo_off, rr + hi_off] in tile rows
-        const int lo_off = kind == 0 ? -P + alo : -P - dy - ahi;
-        const int hi_off = kind == 0 ? -P + ahi : -P - dy - alo;
-        const float* gq = p.gqT + (kind == 0 ? row1 : row2);
-        for (int e = e0; e < e1; e += 4) {
-            int packed[4];
-            float val[4];
+        lo_off[kind] = kind == 0 ? -P + alo : -P - dy - ahi;
+        hi_off[kind] = kind == 0 ? -P + ahi : -P - dy - alo;
+        gq[kind] = p.gqT + (kind == 0 ? row1 : row2);
+    }
+    int n_items = 0;
+    while (e0[0] < e1[0] || e0[1] < e1[1]) {
+        int packed[2][NB];
+        float val[2][NB];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                packed[m] = e + m < e1 ? ent[e + m] : -1;
-                val[m] = packed[m] >= 0 ? __ldg(gq + (packed[m] >> 8)) : 0.f;
+        for (int kind = 0; kind < 2; ++kind)
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                packed[kind][m] = e0[kind] + m < e1[kind] ? ent[e0[kind] + m] : -1;
+                val[kind][m] = packed[kind][m] >= 0 ? __ldg(gq[kind] + (packed[kind][m] >> 8)) : 0.f;
             }
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                if (packed[m] < 0) continue;
-                const int rr = packed[m] & 255;
-                int r0 = rr + lo_off, r1 = rr + hi_off;
+        for (int kind = 0; kind < 2; ++kind) {
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                if (packed[kind][m] < 0) continue;
+                const int rr = packed[kind][m] & 255;
+                int r0 = rr + lo_off[kind], r1 = rr + hi_off[kind];
                 r0 = r0 < 0 ? 0 : r0;
                 r1 = r1 > Cfg::ROWS - 1 ? Cfg::ROWS - 1 : r1;
                 if (r0 > r1) continue;
-                ucol[r0] += val[m];
-                ucol[r1 + 1] -= val[m];
+                ucol[r0] += val[kind][m];
+                ucol[r1 + 1] -= val[kind][m];
                 ++n_items;
             }
+            e0[kind] += NB;
         }
     }
     if (n_items == 0) return;  // column stays exactly zero

@@ -99,17 +99,29 @@ __device__ __forceinline__ void load_plane_tile(const T* img, float* tile, int H
         const int X = Xcol0 + lane + 32 * m;
         sx[m] = (X >= 0 && X < Wp && lane + 32 * m < Cfg::IPITCH) ? reflect_idx(X - P, W) : -1;
     }
-    for (int rr = warp; rr < 3 * Cfg::IROWS; rr += nwarps) {
-        const int c = rr / Cfg::IROWS, row = rr - c * Cfg::IROWS;
-        const int Y = Yrow0 + row;
-        const bool rowok = Y >= 0 && Y < Hp;
-        const T* src = img + ((long long)c * H + (rowok ? reflect_idx(Y - P, H) : 0)) * W;
-        float v[NCOLIT];
+    // RU rows per step: RU * NCOLIT independent global loads in flight per thread
+    constexpr int RU = 4;
+    for (int rr0 = warp * RU; rr0 < 3 * Cfg::IROWS; rr0 += nwarps * RU) {
+        float v[RU][NCOLIT];
 #pragma unroll
-        for (int m = 0; m < NCOLIT; ++m) v[m] = (rowok && sx[m] >= 0) ? load_as_float(src + sx[m]) : 0.f;
+        for (int u = 0; u < RU; ++u) {
+            const int rr = rr0 + u;
+            const int c = rr / Cfg::IROWS, row = rr - c * Cfg::IROWS;
+            const int Y = Yrow0 + row;
+            const bool rowok = rr < 3 * Cfg::IROWS && Y >= 0 && Y < Hp;
+            const T* src = img + ((long long)c * H + (rowok ? reflect_idx(Y - P, H) : 0)) * W;
 #pragma unroll
-        for (int m = 0; m < NCOLIT; ++m)
-            if (lane + 32 * m < Cfg::IPITCH) tile[rr * Cfg::IPITCH + lane + 32 * m] = v[m];
+            for (int m = 0; m < NCOLIT; ++m) v[u][m] = (rowok && sx[m] >= 0) ? load_as_float(src + sx[m]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int rr = rr0 + u;
+            if (rr < 3 * Cfg::IROWS) {
+#pragma unroll
+                for (int m = 0; m < NCOLIT; ++m)
+                    if (lane + 32 * m < Cfg::IPITCH) tile[rr * Cfg::IPITCH + lane + 32 * m] = v[u][m];
+            }
+        }
     }
 }
 
