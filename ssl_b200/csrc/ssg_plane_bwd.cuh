@@ -94,65 +94,86 @@ __global__ void __launch_bounds__(256) plane_bwd_lists_kernel(PlaneBwdParams p, 
     }
 }
 
-// Build one column of one sparse plane: the thread owns u[column][0..63].
-// Every edge pixel that lands in this column covers a run of rows [r0, r1] (the v-direction of the
-// box); it is entered as +val at r0 and -val at r1+1 and the column is then prefix-summed in place,
-// so the cost per edge pixel is two shared-memory updates instead of up to 2K+1.
-template <typename Cfg>
-__device__ __forceinline__ void place_column(const PlaneBwdParams& p, const int32_t* cols, const int32_t* ent,
-                                             float* ucol, int xu, int dy, int dx) {
+// Building one column of one sparse plane (the thread owns u[column][0..ROWS-1]) is split in two so
+// that the loads of dL/dq can be issued one chunk ahead and fly while the sweep of the current chunk
+// computes:  place_fetch (entries + loads into registers)  ...sweep...  place_apply.
+//
+// Every edge pixel that lands in the column covers a run of rows [r0, r1] (the v-direction of the box);
+// it is entered as +val at r0 and -val at r1+1 and the column is then prefix-summed in place, so the
+// cost per edge pixel is two shared-memory updates instead of up to 2K+1.
+template <int NB>
+struct PlaceFetch {
+    int packed[2][NB];
+    float val[2][NB];
+    int e0[2], e1[2];      // entries not covered by the prefetched batch: [e0 + NB, e1)
+    int lo_off[2], hi_off[2];
+    const float* gq[2];
+};
+
+template <typename Cfg, int NB>
+__device__ __forceinline__ void place_fetch(const PlaneBwdParams& p, const int32_t* cols, const int32_t* ent, int xu,
+                                            int dy, int dx, PlaceFetch<NB>& f) {
     using BC = PlaneBwdCfg<Cfg>;
     constexpr int P = Cfg::P, K = Cfg::K;
     const int alo = rng_lo(dy, P, K), ahi = rng_hi(dy, P, K);
     const int blo = rng_lo(dx, P, K), bhi = rng_hi(dx, P, K);
     const long long row1 = (long long)((dy + P) * Cfg::KS + dx + P) * p.cap;
     const long long row2 = (long long)((-dy + P) * Cfg::KS + (-dx) + P) * p.cap;
-    float4* ucol4 = reinterpret_cast<float4*>(ucol);
-#pragma unroll
-    for (int i = 0; i < BC::U_COL / 4; ++i) ucol4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // Both kinds are walked together, NB entries of each per round, so that up to 2*NB loads of dL/dq are
-    // in flight before the first one is consumed (the loads are what this phase waits for).
-    constexpr int NB = 6;
-    int e0[2], e1[2], lo_off[2], hi_off[2];
-    const float* gq[2];
 #pragma unroll
     for (int kind = 0; kind < 2; ++kind) {
         // region column holding the edge pixels that land in u-column xu
         const int pcol = kind == 0 ? xu - blo + P : xu + dx + bhi + P;
         const bool ok = pcol >= 0 && pcol < BC::RCOLS;
-        e0[kind] = ok ? cols[pcol] : 0;
-        e1[kind] = ok ? cols[pcol + 1] : 0;
+        f.e0[kind] = ok ? cols[pcol] : 0;
+        f.e1[kind] = ok ? cols[pcol + 1] : 0;
         // rows covered by an entry at region row rr: [rr + lo_off, rr + hi_off] in tile rows
-        lo_off[kind] = kind == 0 ? -P + alo : -P - dy - ahi;
-        hi_off[kind] = kind == 0 ? -P + ahi : -P - dy - alo;
-        gq[kind] = p.gqT + (kind == 0 ? row1 : row2);
+        f.lo_off[kind] = kind == 0 ? -P + alo : -P - dy - ahi;
+        f.hi_off[kind] = kind == 0 ? -P + ahi : -P - dy - alo;
+        f.gq[kind] = p.gqT + (kind == 0 ? row1 : row2);
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            f.packed[kind][m] = f.e0[kind] + m < f.e1[kind] ? ent[f.e0[kind] + m] : -1;
+            f.val[kind][m] = f.packed[kind][m] >= 0 ? __ldg(f.gq[kind] + (f.packed[kind][m] >> 8)) : 0.f;
+        }
     }
+}
+
+template <typename Cfg>
+__device__ __forceinline__ int place_entry(float* ucol, int packed, float val, int lo_off, int hi_off) {
+    if (packed < 0) return 0;
+    const int rr = packed & 255;
+    int r0 = rr + lo_off, r1 = rr + hi_off;
+    r0 = r0 < 0 ? 0 : r0;
+    r1 = r1 > Cfg::ROWS - 1 ? Cfg::ROWS - 1 : r1;
+    if (r0 > r1) return 0;
+    ucol[r0] += val;
+    ucol[r1 + 1] -= val;
+    return 1;
+}
+
+template <typename Cfg, int NB>
+__device__ __forceinline__ void place_apply(const int32_t* ent, float* ucol, const PlaceFetch<NB>& f) {
+    using BC = PlaneBwdCfg<Cfg>;
+    float4* ucol4 = reinterpret_cast<float4*>(ucol);
+#pragma unroll
+    for (int i = 0; i < BC::U_COL / 4; ++i) ucol4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     int n_items = 0;
-    while (e0[0] < e1[0] || e0[1] < e1[1]) {
-        int packed[2][NB];
-        float val[2][NB];
 #pragma unroll
-        for (int kind = 0; kind < 2; ++kind)
+    for (int kind = 0; kind < 2; ++kind) {
 #pragma unroll
-            for (int m = 0; m < NB; ++m) {
-                packed[kind][m] = e0[kind] + m < e1[kind] ? ent[e0[kind] + m] : -1;
-                val[kind][m] = packed[kind][m] >= 0 ? __ldg(gq[kind] + (packed[kind][m] >> 8)) : 0.f;
+        for (int m = 0; m < NB; ++m)
+            n_items += place_entry<Cfg>(ucol, f.packed[kind][m], f.val[kind][m], f.lo_off[kind], f.hi_off[kind]);
+        // columns with more than NB entries of a kind (dense masks): the rest, in batches of 4
+        for (int e = f.e0[kind] + NB; e < f.e1[kind]; e += 4) {
+            int packed[4];
+            float val[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                packed[m] = e + m < f.e1[kind] ? ent[e + m] : -1;
+                val[m] = packed[m] >= 0 ? __ldg(f.gq[kind] + (packed[m] >> 8)) : 0.f;
             }
 #pragma unroll
-        for (int kind = 0; kind < 2; ++kind) {
-#pragma unroll
-            for (int m = 0; m < NB; ++m) {
-                if (packed[kind][m] < 0) continue;
-                const int rr = packed[kind][m] & 255;
-                int r0 = rr + lo_off[kind], r1 = rr + hi_off[kind];
-                r0 = r0 < 0 ? 0 : r0;
-                r1 = r1 > Cfg::ROWS - 1 ? Cfg::ROWS - 1 : r1;
-                if (r0 > r1) continue;
-                ucol[r0] += val[kind][m];
-                ucol[r1 + 1] -= val[kind][m];
-                ++n_items;
-            }
-            e0[kind] += NB;
+            for (int m = 0; m < 4; ++m) n_items += place_entry<Cfg>(ucol, packed[m], val[m], f.lo_off[kind], f.hi_off[kind]);
         }
     }
     if (n_items == 0) return;  // column stays exactly zero
@@ -219,11 +240,17 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
 #pragma unroll
         for (int j = 0; j < GJ; ++j) box_carry_reset(carry[j]);
         const int ticket = idy * NWP + wp;
+        constexpr int NB = 4;  // registers are tight: 13 warps => 128 per thread
+        PlaceFetch<NB> pf;
+        if (pj < GJ) place_fetch<Cfg, NB>(p, cols, ent, c8, dy, GC::DX0 + pj, pf);
         for (int k = 0; k < BC::NCHB; ++k) {
             worker_sync<Cfg::ROWS>(wp);  // the previous chunk's sweep has finished reading u
-            // 1. build the chunk's 8 u-columns of every plane (one thread per column; it also clears it)
-            if (pj < GJ)
-                place_column<Cfg>(p, cols, ent, uworker + pj * BC::U_PLANE + c8 * BC::U_COL, 8 * k + c8, dy, GC::DX0 + pj);
+            // 1. build the chunk's 8 u-columns of every plane (one thread per column; it also clears it),
+            //    then start the loads of the next chunk's columns: they fly during the sweep below
+            if (pj < GJ) {
+                place_apply<Cfg, NB>(ent, uworker + pj * BC::U_PLANE + c8 * BC::U_COL, pf);
+                if (k + 1 < BC::NCHB) place_fetch<Cfg, NB>(p, cols, ent, 8 * (k + 1) + c8, dy, GC::DX0 + pj, pf);
+            }
             worker_sync<Cfg::ROWS>(wp);
             // 2. h-direction + products
             float acc[3][8];
