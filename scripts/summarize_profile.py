@@ -63,17 +63,34 @@ def main():
         hdr, units = rows[0], rows[1]
         out += ["## `ncu --set full --clock-control none` capture (per launch)", ""]
         seen = set()
+        traffic = {}
+        stage_of = {"ssg_plane_fwd_kernel": "ssg_plane_fwd", "ssg_plane_bwd_kernel": "ssg_plane_bwd",
+                    "ssg_point_fwd": "ssg_point_fwd", "ssg_point_bwd": "ssg_point_bwd"}
+
+        def to_bytes(v, u):
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            return float(v.replace(",", "")) * scale
+
         for r in rows[2:]:
             name = r[hdr.index("Kernel Name")]
             if name in seen:
                 continue
             seen.add(name)
+            for frag, stage in stage_of.items():
+                if frag in name and "dram__bytes_read.sum" in hdr:
+                    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+                    traffic[stage] = to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
             out += [f"### `{name}`", "", "| metric | value | unit |", "|---|---|---|"]
             for k in KEYS:
                 if k in hdr:
                     i = hdr.index(k)
                     out.append(f"| {k} | {r[i]} | {units[i]} |")
             out.append("")
+        if traffic:
+            # bench.py reads this for roofline.traffic (dram read + write bytes per launch of the kernel)
+            with open(os.path.join("profiles", "dram_traffic.json"), "w") as f:
+                json.dump(traffic, f, indent=1)
+            out += ["DRAM traffic per launch (read + write, bytes): " + json.dumps(traffic), ""]
     os.makedirs("profiles", exist_ok=True)
     path = os.path.join("profiles", tag + ".md")
     open(path, "w").write("\n".join(out) + "\n")
