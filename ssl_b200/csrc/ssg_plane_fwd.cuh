@@ -356,6 +356,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(PlaneFwd
         case 2: if constexpr (Cfg::NDXG > 2) run_group_fwd<Cfg, 2>(p, tile, splanes, ustart_s, slot_rc, which); break;
         case 3: if constexpr (Cfg::NDXG > 3) run_group_fwd<Cfg, 3>(p, tile, splanes, ustart_s, slot_rc, which); break;
         case 4: if constexpr (Cfg::NDXG > 4) run_group_fwd<Cfg, 4>(p, tile, splanes, ustart_s, slot_rc, which); break;
+        case 5: if constexpr (Cfg::NDXG > 5) run_group_fwd<Cfg, 5>(p, tile, splanes, ustart_s, slot_rc, which); break;
+        case 6: if constexpr (Cfg::NDXG > 6) run_group_fwd<Cfg, 6>(p, tile, splanes, ustart_s, slot_rc, which); break;
         default: break;
     }
 }

@@ -351,6 +351,8 @@ size_t point_loss_workspace_bytes(int ks, int max_edges) {
 // kernels win (measured crossover, profiles/).
 bool use_plane_path(int path, int B, int C, int H, int W, int ks, int kw, int max_edges) {
     if (path == SSL_B200_PATH_POINT || !plane_supported(ks, kw, C)) return false;
+    // backward column lists pack (slot << 8 | row): slots must stay below 2^23
+    if ((long long)max_edges + 3ll * ((long long)B * H * W / 448 + 64) >= (1ll << 23)) return false;
     if (path == SSL_B200_PATH_PLANE) return true;
     return (double)max_edges >= 0.02 * (double)B * H * W;
 }
@@ -377,6 +379,8 @@ extern "C" int ssl_b200_loss_forward_backward(const void* sr, const void* gt, in
                  "workspace too small");
     SSLB_REQUIRE(path != SSL_B200_PATH_PLANE || plane_supported(ks, kw, C), "no plane kernels for k_s=%d k_w=%d C=%d",
                  ks, kw, C);
+    SSLB_REQUIRE(path != SSL_B200_PATH_PLANE || max_edges <= 0 || use_plane_path(path, B, C, H, W, ks, kw, max_edges),
+                 "batch too large for the plane path (%d edge pixels); use SSL_B200_PATH_AUTO or _POINT", max_edges);
     if (int e = check_sizes(ks, kw, H, W, C)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     SSLB_CUDA(cudaMemsetAsync(terms, 0, 3 * sizeof(double), st));
