@@ -302,20 +302,26 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
 #pragma unroll
                         for (int e = 0; e < 4; ++e) eo[e] = __ldg(eout + (long long)(gs + e) * (NC * NC) + cls);
                     }
+                    // all 4 x (2K+1) ring reads are issued before the first addition (no branch between the
+                    // slots, so the loads of one slot do not wait for the sums of the previous one); rows
+                    // re-K..re+K always lie inside the worker's rows, the a-range only selects what is added
+                    float v[4][2 * K + 1];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int rc = rcs[e] >= 0 ? rcs[e] : (K << 8);  // padding slot: any valid address
+                        const int re = rc >> 8, ex = rc & 255;
+                        const float* sp = myplane + re * Cfg::SRP + ((ex + coff) & (Cfg::RING - 1));
+#pragma unroll
+                        for (int a = -K; a <= K; ++a) v[e][a + K] = sp[a * Cfg::SRP];
+                    }
                     float out[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int rc = rcs[e];
                         float acc = 0.f;
-                        if (rc >= 0) {
-                            const int re = rc >> 8, ex = rc & 255;
-                            const float* sp = myplane + re * Cfg::SRP + ((ex + coff) & (Cfg::RING - 1));
 #pragma unroll
-                            for (int a = -K; a <= K; ++a)
-                                if (a >= alo && a <= ahi) acc += sp[a * Cfg::SRP];
-                            acc += eo[e];
-                        }
-                        out[e] = acc;
+                        for (int a = -K; a <= K; ++a)
+                            if (a >= alo && a <= ahi) acc += v[e][a + K];
+                        out[e] = rcs[e] >= 0 ? acc + eo[e] : 0.f;
                     }
                     *reinterpret_cast<float4*>(qT + qrow + gs) = make_float4(out[0], out[1], out[2], out[3]);
                 }
