@@ -133,6 +133,17 @@ int ssl_b200_plane_rows_forward(const void* image, const void* image2, int dtype
                                 const int32_t* edges, const int32_t* n_edges_dev, int max_edges, int ks, int kw,
                                 float* rows, float* rows2, void* workspace, size_t workspace_bytes, void* stream);
 
+/* In place: raw distances (ROWS_RAW) -> `rows_mode` rows; the tail of loss_util.py:234-243. */
+int ssl_b200_rows_from_distance(float* rows, const int32_t* n_edges_dev, int max_edges, int ks, int kw, int C,
+                                float sigma, float eps, int rows_mode, void* stream);
+
+/* == ssl_b200_ssg_rows_backward through the plane kernels: gq = dL/dq rows [max_edges, ks*ks] in the order of
+ * `edges`; grad_image fp32 [B,C,H,W] is OVERWRITTEN.  n_edges_dev must be given (counts[0]). */
+size_t ssl_b200_plane_rows_backward_workspace_bytes(int B, int H, int W, int ks, int kw, int max_edges);
+int ssl_b200_plane_rows_backward(const void* image, int dtype, int B, int C, int H, int W, const int32_t* edges,
+                                 const int32_t* n_edges_dev, int max_edges, int ks, int kw, const float* gq,
+                                 float* grad_image, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- whole step ------------------------------------------------------------------------- */
 
 /* The reference training-step block (realesrganssl_model.py:378-430: per-image loop, two

@@ -44,6 +44,12 @@ SIGNATURES = {
     "ssl_b200_plane_rows_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                              _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                                              _c_size_t, _c_void_p]),
+    "ssl_b200_rows_from_distance": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,
+                                             _c_int, _c_void_p]),
+    "ssl_b200_plane_rows_backward_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
+    "ssl_b200_plane_rows_backward": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
+                                              _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t,
+                                              _c_void_p]),
     "ssl_b200_loss_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
     "ssl_b200_loss_forward_backward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                                 _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_float,

@@ -122,6 +122,15 @@ __global__ void __launch_bounds__(256) plane_mark_edges_kernel(PlaneListParams p
         p.out.slot_map[p.edges[i]] = -2;
 }
 
+// slot_ref[slot] = position of the slot's pixel in the flat edge list (after the unit passes)
+__global__ void __launch_bounds__(256) plane_slot_ref_kernel(PlaneListParams p, int32_t* slot_ref) {
+    const int mc = edge_count(p.n_edges_dev, p.max_edges);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc; i += gridDim.x * blockDim.x) {
+        const int slot = p.out.slot_map[p.edges[i]];
+        if (slot >= 0 && slot < p.capacity) slot_ref[slot] = i;
+    }
+}
+
 __device__ __forceinline__ bool unit_is_edge(const PlaneListParams& p, int b, int y, int x) {
     if (p.mask) return mask_is_edge(p.mask, p.mask_channels, p.stride, p.g.H, p.g.W, b, y, x);
     return p.out.slot_map[(b * p.g.H + y) * p.g.W + x] != -1;

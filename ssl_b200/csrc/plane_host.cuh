@@ -157,6 +157,52 @@ inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int
     return l;
 }
 
+// dL/dq (offset-major, gqT) + per-class sums (gcls) -> dL/dimage.  Shared by the fused step and by the
+// rows backward of the operator API.
+template <typename Cfg>
+inline int launch_plane_backward_cfg(const void* img, int dtype, int B, int H, int W, const PlaneLists& lists,
+                                     const PlaneStepLayout& l, char* ws, const float* gqT, const float* gcls,
+                                     float* grad_out, cudaStream_t st) {
+    using BG = PlaneBwdGeom<Cfg>;
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    PlaneBwdParams bp{};
+    bp.img = img; bp.gqT = gqT;
+    int32_t* tcols = reinterpret_cast<int32_t*>(ws + l.off_tcols);
+    int32_t* tent = reinterpret_cast<int32_t*>(ws + l.off_tent);
+    bp.tile_cols = tcols; bp.tile_ent = tent;
+    bp.gpart = reinterpret_cast<float*>(ws + l.off_gpart);
+    bp.slot_map = lists.slot_map;
+    bp.B = B; bp.H = H; bp.W = W; bp.cap = l.cap;
+    bp.ntyb = l.ntyb; bp.ntxb = l.ntxb; bp.HT = l.HT; bp.WT = l.WT;
+    {
+        StageTimer timer(kStagePlaneBwdLists, st);
+        plane_bwd_lists_kernel<BG><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tent);
+    }
+    const size_t smem = plane_bwd_smem_bytes<BG>();
+    SSLB_REQUIRE(smem <= (size_t)di.max_smem_optin, "plane backward needs %zu B of shared memory", smem);
+    PlaneFinishParams fp{};
+    fp.img = img; fp.gpart = bp.gpart; fp.wtab = reinterpret_cast<float*>(ws + l.off_wtab);
+    fp.slot_map = lists.slot_map; fp.grad = grad_out;
+    fp.wsum = reinterpret_cast<float*>(ws + l.off_wsum);
+    fp.B = B; fp.H = H; fp.W = W; fp.HT = l.HT; fp.WT = l.WT; fp.n_parts = BG::NDXG; fp.cap = l.cap;
+    const long long npx = (long long)B * H * W;
+    SSLB_DISPATCH_DTYPE(dtype, T, {
+        auto k = ssg_plane_bwd_kernel<T, BG>;
+        SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            StageTimer timer(kStagePlaneBwd, st);
+            k<<<dim3(l.n_btiles, BG::NDXG), BG::THREADS, smem, st>>>(bp);
+        }
+        StageTimer timer(kStageFinish, st);
+        plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(gcls, lists.counts, l.cap,
+                                                               reinterpret_cast<float*>(ws + l.off_wtab));
+        plane_wsum_kernel<Cfg><<<dim3(l.WT / 16, l.HT / 16, B), 256, 0, st>>>(fp);
+        plane_finish_kernel<T, Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
+    });
+    return check_launch("plane_backward", 5);
+}
+
 template <typename Cfg>
 inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int B, int H, int W, const int32_t* edges,
                                  const int32_t* counts, int max_edges, float sigma, float eps, int rows_mode,
@@ -195,41 +241,37 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
     }
     if (int e = check_launch("row_loss_t", 2)) return e;
     if (!grad_sr) return 0;
-    PlaneBwdParams bp{};
-    bp.img = sr; bp.gqT = q_sr;
-    int32_t* tcols = reinterpret_cast<int32_t*>(ws + l.off_tcols);
-    int32_t* tent = reinterpret_cast<int32_t*>(ws + l.off_tent);
-    bp.tile_cols = tcols; bp.tile_ent = tent;
-    bp.gpart = reinterpret_cast<float*>(ws + l.off_gpart);
-    bp.slot_map = lists.slot_map;
-    bp.B = B; bp.H = H; bp.W = W; bp.cap = l.cap;
-    bp.ntyb = l.ntyb; bp.ntxb = l.ntxb; bp.HT = l.HT; bp.WT = l.WT;
+    return launch_plane_backward_cfg<Cfg>(sr, dtype, B, H, W, lists, l, ws, q_sr, rp.gcls, grad_sr, st);
+}
+
+// Rows backward behind the reference's operator API (similarity_map / compute_similarity): dL/dq rows in the
+// reference's order [n][L] -> dL/dimage, through the plane kernels.  Workspace = plane_step_layout(...).
+template <typename Cfg>
+inline int launch_plane_rows_backward_cfg(const void* img, int dtype, int B, int H, int W, const int32_t* edges,
+                                          const int32_t* counts, int max_edges, const float* gq_rows, float* grad,
+                                          void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, 2 * di.sm_count, true);
+    SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
+    char* ws = static_cast<char*>(workspace);
+    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st)) return e;
+    const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
+    float* gqT = reinterpret_cast<float*>(ws + l.off_q[0]);
+    float* gcls = reinterpret_cast<float*>(ws + l.off_gcls);
+    int32_t* slot_ref = reinterpret_cast<int32_t*>(ws + l.off_q[1]);  // the GT rows buffer is free here
     {
-        StageTimer timer(kStagePlaneBwdLists, st);
-        plane_bwd_lists_kernel<BG><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tent);
+        StageTimer timer(kStageRowLoss, st);
+        PlaneListParams lp{};
+        lp.edges = edges; lp.n_edges_dev = counts; lp.max_edges = max_edges; lp.capacity = l.cap; lp.out = lists;
+        const int nb = (max_edges + 255) / 256 < 2048 ? (max_edges + 255) / 256 : 2048;
+        plane_slot_ref_kernel<<<nb, 256, 0, st>>>(lp, slot_ref);
+        plane_rows_to_slots_kernel<<<di.sm_count * 4, 256, 0, st>>>(gq_rows, lists.slot_pix, slot_ref, lists.counts, l.cap,
+                                                                   Cfg::L, gqT);
+        plane_class_sums_kernel<<<di.sm_count * 8, 256, 0, st>>>(gqT, lists.counts, l.cap, Cfg::KS, Cfg::P, Cfg::K, gcls);
     }
-    const size_t smem = plane_bwd_smem_bytes<BG>();
-    SSLB_REQUIRE(smem <= (size_t)di.max_smem_optin, "plane backward needs %zu B of shared memory", smem);
-    PlaneFinishParams fp{};
-    fp.img = sr; fp.gpart = bp.gpart; fp.wtab = reinterpret_cast<float*>(ws + l.off_wtab);
-    fp.slot_map = lists.slot_map; fp.grad = grad_sr;
-    fp.wsum = reinterpret_cast<float*>(ws + l.off_wsum);
-    fp.B = B; fp.H = H; fp.W = W; fp.HT = l.HT; fp.WT = l.WT; fp.n_parts = BG::NDXG; fp.cap = l.cap;
-    const long long npx = (long long)B * H * W;
-    SSLB_DISPATCH_DTYPE(dtype, T, {
-        auto k = ssg_plane_bwd_kernel<T, BG>;
-        SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        {
-            StageTimer timer(kStagePlaneBwd, st);
-            k<<<dim3(l.n_btiles, BG::NDXG), BG::THREADS, smem, st>>>(bp);
-        }
-        StageTimer timer(kStageFinish, st);
-        plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(rp.gcls, lists.counts, l.cap,
-                                                               reinterpret_cast<float*>(ws + l.off_wtab));
-        plane_wsum_kernel<Cfg><<<dim3(l.WT / 16, l.HT / 16, B), 256, 0, st>>>(fp);
-        plane_finish_kernel<T, Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
-    });
-    return check_launch("plane_backward", 5);
+    if (int e = check_launch("plane_rows_to_slots", 3)) return e;
+    return launch_plane_backward_cfg<Cfg>(img, dtype, B, H, W, lists, l, ws, gqT, gcls, grad, st);
 }
 
 }  // namespace sslb

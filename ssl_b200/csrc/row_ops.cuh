@@ -118,6 +118,27 @@ __global__ void __launch_bounds__(kRowThreads) rows_chain_kernel(const float* ro
     }
 }
 
+// Raw distances -> exp / normalised rows, in place (loss_util.py:234-243); one block per row.
+__global__ void __launch_bounds__(kRowThreads) rows_finish_kernel(float* rows, const int32_t* n_edges_dev, int max_edges,
+                                                                 int L, float denom, float sigma, float eps, int mode) {
+    __shared__ float red[32];
+    const int mc = edge_count(n_edges_dev, max_edges);
+    for (int n = blockIdx.x; n < mc; n += gridDim.x) {
+        float* q = rows + (long long)n * L;
+        float z = 0.f;
+        for (int d = threadIdx.x; d < L; d += kRowThreads) {
+            const float e = expf(-1.0f * (q[d] / denom) / sigma);
+            q[d] = e;
+            z += e;
+        }
+        if (mode == SSL_B200_ROWS_NORM) {
+            z = block_sum(z, red);
+            const float r = 1.0f / (z + eps);
+            for (int d = threadIdx.x; d < L; d += kRowThreads) q[d] = r * q[d];
+        }
+    }
+}
+
 // generate_mask.py:22-31 on the GT crop.  One thread per pixel.
 template <typename T>
 __global__ void __launch_bounds__(256) laplacian_mask_kernel(const T* gt, int B, int H, int W, float threshold,

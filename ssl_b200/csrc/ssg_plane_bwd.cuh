@@ -375,6 +375,40 @@ __global__ void __launch_bounds__(128) plane_wtab_kernel(const float* gcls, cons
     }
 }
 
+// rows in the reference's order [n][L] -> offset-major gqT[L][cap] (padding slots get zeros).
+// One thread per slot walks its row; consecutive threads write consecutive slots.
+__global__ void __launch_bounds__(256) plane_rows_to_slots_kernel(const float* rows, const int32_t* slot_pix,
+                                                                  const int32_t* slot_ref, const int32_t* counts, int cap,
+                                                                  int L, float* gqT) {
+    const int n_slots = min(counts[0], cap);
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
+        const bool real = slot_pix[slot] >= 0;
+        const float* src = rows + (long long)(real ? slot_ref[slot] : 0) * L;
+        for (int d = 0; d < L; ++d) gqT[(long long)d * cap + slot] = real ? __ldg(src + d) : 0.f;
+    }
+}
+
+// gcls[class][slot] = sum of gqT over the offsets of a clip class (what row_loss_t_kernel emits in the
+// fused step); classes with nothing out of area stay zero.  One thread per (slot, class).
+__global__ void __launch_bounds__(256) plane_class_sums_kernel(const float* gqT, const int32_t* counts, int cap, int KS,
+                                                               int P, int K, float* gcls) {
+    const int n_slots = min(counts[0], cap);
+    const int NC = 2 * K + 1, U = P - K;
+    const long long total = (long long)n_slots * NC * NC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int slot = (int)(i % n_slots), c = (int)(i / n_slots);
+        const int ca = c / NC, cb = c % NC;
+        float acc = 0.f;
+        if (ca != K || cb != K) {
+            const int dy0 = ca < K ? ca - P : (ca > K ? U + (ca - K) : -U), dy1 = ca == K ? U : dy0;
+            const int dx0 = cb < K ? cb - P : (cb > K ? U + (cb - K) : -U), dx1 = cb == K ? U : dx0;
+            for (int dy = dy0; dy <= dy1; ++dy)
+                for (int dx = dx0; dx <= dx1; ++dx) acc += gqT[(long long)((dy + P) * KS + dx + P) * cap + slot];
+        }
+        gcls[(long long)c * cap + slot] = acc;
+    }
+}
+
 struct PlaneFinishParams {
     const void* img;
     const float* gpart;       // [NDXG][B][3][HT][WT]

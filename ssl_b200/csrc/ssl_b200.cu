@@ -313,6 +313,44 @@ extern "C" int ssl_b200_plane_rows_forward(const void* image, const void* image2
     });
 }
 
+extern "C" int ssl_b200_rows_from_distance(float* rows, const int32_t* n_edges_dev, int max_edges, int ks, int kw,
+                                           int C, float sigma, float eps, int rows_mode, void* stream) {
+    SSLB_REQUIRE(rows, "null pointer");
+    if (rows_mode == SSL_B200_ROWS_RAW || max_edges <= 0) return 0;
+    SSLB_REQUIRE(sigma > 0.f, "sigma must be positive");
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const int blocks = min(max_edges, di.sm_count * 16);
+    rows_finish_kernel<<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(rows, n_edges_dev, max_edges, ks * ks,
+                                                                        (float)C * (float)(kw * kw), sigma, eps, rows_mode);
+    return check_launch("rows_finish");
+}
+
+extern "C" size_t ssl_b200_plane_rows_backward_workspace_bytes(int B, int H, int W, int ks, int kw, int max_edges) {
+    if (!plane_supported(ks, kw, 3) || B < 1 || H < 1 || W < 1 || max_edges < 0) return 0;
+    DeviceInfo di;
+    const int loss_blocks = 2 * (device_info(&di) ? 148 : di.sm_count);
+    SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, { return plane_step_layout<Cfg>(B, H, W, max_edges, loss_blocks, true).total; });
+}
+
+extern "C" int ssl_b200_plane_rows_backward(const void* image, int dtype, int B, int C, int H, int W,
+                                            const int32_t* edges, const int32_t* n_edges_dev, int max_edges, int ks,
+                                            int kw, const float* gq, float* grad_image, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+    SSLB_REQUIRE(image && edges && n_edges_dev && gq && grad_image && workspace, "null pointer");
+    SSLB_REQUIRE(plane_supported(ks, kw, C), "no plane kernels for k_s=%d k_w=%d C=%d", ks, kw, C);
+    if (int e = check_sizes(ks, kw, H, W, C)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (max_edges <= 0) {
+        SSLB_CUDA(cudaMemsetAsync(grad_image, 0, sizeof(float) * (size_t)B * C * H * W, st));
+        return 0;
+    }
+    SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, {
+        return launch_plane_rows_backward_cfg<Cfg>(image, dtype, B, H, W, edges, n_edges_dev, max_edges, gq, grad_image,
+                                                   workspace, workspace_bytes, st);
+    });
+}
+
 // ---- whole step ---------------------------------------------------------------------------
 
 namespace {

@@ -143,13 +143,54 @@ def _rows_backward(img, el: EdgeList, n: int, ks, kw, gq, n_dev=True):
     return grad
 
 
+def _use_plane(path: str, b: int, c: int, h: int, w: int, ks: int, kw: int, n: int) -> bool:
+    """Same rule as the library's SSL_B200_PATH_AUTO: plane kernels when they exist for (k_s, k_w, C) and the
+    mask holds at least 2 % of the pixels (they pay per image pixel, the point kernels per edge pixel)."""
+    if path == "point" or not _lib.load().ssl_b200_plane_supported(ks, kw, c):
+        if path == "plane":
+            raise ValueError(f"no plane kernels for k_s={ks} k_w={kw} C={c}")
+        return False
+    return path == "plane" or n >= 0.02 * b * h * w
+
+
+def _plane_rows_forward(img, el: EdgeList, n: int, ks, kw, sigma, eps, mode):
+    b, c, h, w = img.shape
+    rows = torch.empty(n, ks * ks, dtype=torch.float32, device=img.device)
+    if n:
+        lib = _lib.load()
+        ws_bytes = int(lib.ssl_b200_plane_rows_workspace_bytes(b, h, w, ks, kw, n))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)
+        with torch.cuda.device(img.device):
+            _lib.call("ssl_b200_plane_rows_forward", _ptr(img), _ptr(None), _lib.dtype_code(img.dtype), b, c, h, w,
+                      _ptr(el.edges), _ptr(el.counts), n, ks, kw, _ptr(rows), _ptr(None), _ptr(ws), ws_bytes, _stream())
+            if mode != ROWS_RAW:
+                _lib.call("ssl_b200_rows_from_distance", _ptr(rows), _ptr(el.counts), n, ks, kw, c, float(sigma),
+                          float(eps), mode, _stream())
+    return rows
+
+
+def _plane_rows_backward(img, el: EdgeList, n: int, ks, kw, gq):
+    b, c, h, w = img.shape
+    grad = torch.zeros(b, c, h, w, dtype=torch.float32, device=img.device)
+    if n:
+        ws_bytes = int(_lib.load().ssl_b200_plane_rows_backward_workspace_bytes(b, h, w, ks, kw, n))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)
+        with torch.cuda.device(img.device):
+            _lib.call("ssl_b200_plane_rows_backward", _ptr(img), _lib.dtype_code(img.dtype), b, c, h, w, _ptr(el.edges),
+                      _ptr(el.counts), n, ks, kw, _ptr(gq), _ptr(grad), _ptr(ws), ws_bytes, _stream())
+    return grad
+
+
 class _SSGRows(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img, el, n, ks, kw, sigma, eps, mode):
+    def forward(ctx, img, el, n, ks, kw, sigma, eps, mode, plane=False):
         img_c = img.contiguous()
-        rows, _ = _rows_forward(img_c, None, el, n, ks, kw, sigma, eps, mode)
+        if plane:
+            rows = _plane_rows_forward(img_c, el, n, ks, kw, sigma, eps, mode)
+        else:
+            rows, _ = _rows_forward(img_c, None, el, n, ks, kw, sigma, eps, mode)
         ctx.save_for_backward(img_c, rows)
-        ctx.el, ctx.n, ctx.cfg = el, n, (ks, kw, sigma, mode)
+        ctx.el, ctx.n, ctx.cfg, ctx.plane = el, n, (ks, kw, sigma, mode), plane
         return rows
 
     @staticmethod
@@ -163,17 +204,18 @@ class _SSGRows(torch.autograd.Function):
             with torch.cuda.device(img.device):
                 _lib.call("ssl_b200_rows_grad_to_distance_grad", _ptr(rows), _ptr(gq), _ptr(ctx.el.counts), n, ks, kw,
                           img.shape[1], float(sigma), mode, _stream())
-        grad = _rows_backward(img, ctx.el, n, ks, kw, gq)
-        return grad.to(img.dtype), None, None, None, None, None, None, None
+        grad = (_plane_rows_backward if ctx.plane else _rows_backward)(img, ctx.el, n, ks, kw, gq)
+        return grad.to(img.dtype), None, None, None, None, None, None, None, None
 
 
 def ssg_rows(img: torch.Tensor, edge_list: EdgeList, kernel_size_search: int = 25, kernel_size_window: int = 9,
              sigma: float = 0.004, generalization: bool = True, eps: float = 1e-10, raw: bool = False,
-             n: Optional[int] = None) -> torch.Tensor:
+             n: Optional[int] = None, path: str = "auto") -> torch.Tensor:
     """Similarity rows [n, k_s^2] of every listed edge pixel of ``img`` [B,C,H,W]; differentiable in ``img``.
 
     Equals ``torch.cat([similarity_map(img_b, mask_b, ...).getitem() for b ...], dim=1)[0]`` of the
     reference (loss_util.py:165-248).  ``n`` defaults to ``edge_list.count()`` (one 4-byte sync).
+    ``path``: "auto" | "point" | "plane" (which kernel family computes the rows and their backward).
     """
     _require_cuda(img, "img")
     if img.dim() != 4:
@@ -183,8 +225,9 @@ def ssg_rows(img: torch.Tensor, edge_list: EdgeList, kernel_size_search: int = 2
         raise ValueError("edge list was built for a different batch shape")
     _check_kernel_sizes(kernel_size_search, kernel_size_window, h, w)
     n = edge_list.count() if n is None else int(n)
+    plane = _use_plane(path, b, c, h, w, int(kernel_size_search), int(kernel_size_window), n)
     return _SSGRows.apply(img, edge_list, n, int(kernel_size_search), int(kernel_size_window), float(sigma),
-                          float(eps), rows_mode(generalization, raw))
+                          float(eps), rows_mode(generalization, raw), plane)
 
 
 def compute_similarity(image: torch.Tensor, mask: torch.Tensor, psize: int = 25, ksize: int = 9) -> torch.Tensor:
