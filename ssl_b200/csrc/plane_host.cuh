@@ -109,7 +109,7 @@ inline int launch_plane_forward_cfg(const void* img, const void* img2, int dtype
         auto k = ssg_plane_fwd_kernel<T, Cfg>;
         SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         StageTimer timer(kStagePlaneFwd, st);
-        k<<<dim3(tiles, Cfg::NDXG, n_img), Cfg::THREADS, smem, st>>>(p);
+        k<<<dim3(Cfg::NDXG, tiles, n_img), Cfg::THREADS, smem, st>>>(p);
     });
     return check_launch("plane_forward", 2);
 }

@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(PlaneFwd
     int32_t* rc_s = reinterpret_cast<int32_t*>(splanes + Cfg::NPL * Cfg::SPS + 3);  // keep 16-byte alignment below
     rc_s = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(rc_s) + 15) & ~(uintptr_t)15);
     __shared__ int32_t ustart_s[Cfg::UNITS_X + 1];
-    const int t = blockIdx.x;
+    // the dx-groups of one tile are neighbours in launch order: they share the tile's image data in L2
+    const int t = blockIdx.y;
     const int tx = t % p.g.ntx, ty = (t / p.g.ntx) % p.g.nty, b = t / (p.g.ntx * p.g.nty);
     const int unit0 = t * Cfg::UNITS_X;
     const int slot0 = p.lists.unit_start[unit0];
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(PlaneFwd
         for (int i = threadIdx.x; i < slot1 - slot0; i += blockDim.x) rc_s[i] = p.lists.slot_rc[slot0 + i];
     const int32_t* slot_rc = staged ? rc_s : p.lists.slot_rc + slot0;
     __syncthreads();
-    switch (blockIdx.y) {
+    switch (blockIdx.x) {
         case 0: run_group_fwd<Cfg, 0>(p, tile, splanes, ustart_s, slot_rc, which); break;
         case 1: if constexpr (Cfg::NDXG > 1) run_group_fwd<Cfg, 1>(p, tile, splanes, ustart_s, slot_rc, which); break;
         case 2: if constexpr (Cfg::NDXG > 2) run_group_fwd<Cfg, 2>(p, tile, splanes, ustart_s, slot_rc, which); break;
