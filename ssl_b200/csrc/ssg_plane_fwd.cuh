@@ -230,14 +230,20 @@ __device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splane
                 d[j][i] = fmaf(t, t, d[j][i]);
             }
     }
-    float* sp0 = splanes + (wp * Cfg::G) * Cfg::SPS + r * Cfg::SRP + (k & 1) * 8;
+    // Ring column of plane j = sweep column + (K - hi(dx_j)): every plane is then read at column px + 2K, so
+    // the G planes of one edge pixel sit in G consecutive banks for clipped and unclipped dx alike.
+    float* spa = splanes + (wp * Cfg::G) * Cfg::SPS + r * Cfg::SRP + (k & 1) * 8;   // ring half of this chunk
+    float* spb = splanes + (wp * Cfg::G) * Cfg::SPS + r * Cfg::SRP + ((k & 1) ^ 1) * 8;  // the other half
     BoxDispatch<0, GJ>::template run<Cfg, GC::DX0>([&](auto jc, auto lenc) {
         constexpr int j = decltype(jc)::value, len = decltype(lenc)::value;
+        constexpr int shift = Cfg::K - rng_hi(GC::DX0 + j, Cfg::P, Cfg::K);
         float s[8];
         box_last<len>(d[j], carry[j], s);
-        float* sp = sp0 + j * Cfg::SPS;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sp[i] = s[i];
+        for (int i = 0; i < 8; ++i) {
+            if (i + shift < 8) spa[j * Cfg::SPS + i + shift] = s[i];
+            else spb[j * Cfg::SPS + i + shift - 8] = s[i];
+        }
     });
 }
 
@@ -268,7 +274,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
     const bool g_ok = ggrp < NGRP;
     const int g_dx = GC::DX0 + gj;
     const int cb = clip_class(g_dx, P, K);
-    const int coff = K + rng_hi(g_dx, P, K);
+    const int coff = 2 * K;  // ring columns are stored shifted per plane (sweep_chunk_fwd)
     const float* myplane = splanes + (wp * G + gj) * Cfg::SPS;
     for (int dy = wp - P; dy <= P; dy += Cfg::NWP) {
         const int alo = rng_lo(dy, P, K), ahi = rng_hi(dy, P, K);
