@@ -185,6 +185,75 @@ __global__ void __launch_bounds__(256) plane_units_kernel(PlaneListParams p) {
     }
 }
 
+// Emit pass (after the scan), one warp per unit.  The order of a unit's edge pixels inside its slot range is
+// free (slot_map / slot_pix carry the correspondence), so it is chosen for the forward gather: there a warp reads,
+// in one shared-memory instruction, the same ring position of G planes for ~6 consecutive 4-slot groups, and
+// the bank of a slot is h = (SRP * row + column) mod 32.  Slots are counting-sorted by h and dealt out so
+// that consecutive groups get ranks n/6 apart, i.e. banks ~32/6 apart: their G-bank runs do not overlap.
+constexpr int kUnitMaxEdges = 512;
+constexpr int kSpreadRows = 6;
+
+__global__ void __launch_bounds__(256) plane_units_emit_kernel(PlaneListParams p, int srp) {
+    __shared__ int32_t s_rc[8][kUnitMaxEdges], s_pix[8][kUnitMaxEdges];
+    __shared__ uint8_t s_h[8][kUnitMaxEdges];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * 8 + wib;
+    if (warp >= p.g.n_units) return;
+    int b, ty, tx, cx;
+    decode_unit(p.g, warp, b, ty, tx, cx);
+    const int y0 = ty * p.g.TYF, x0 = tx * p.g.TXF + cx * 8;
+    const int ly = lane >> 3, lx = lane & 7;
+    // 1. collect the unit's edge pixels in row-major order
+    int n = 0;
+    for (int yy = 0; yy < p.g.TYF; yy += 4) {
+        const int y = y0 + yy + ly, x = x0 + lx;
+        const bool e = (yy + ly) < p.g.TYF && y < p.g.H && x < p.g.W && unit_is_edge(p, b, y, x);
+        const unsigned ball = __ballot_sync(0xffffffffu, e);
+        if (e) {
+            const int t = n + __popc(ball & ((1u << lane) - 1u));
+            const int re = yy + ly + p.g.K, ex = cx * 8 + lx;
+            s_rc[wib][t] = (re << 8) | ex;
+            s_pix[wib][t] = (b * p.g.H + y) * p.g.W + x;
+            s_h[wib][t] = (uint8_t)((srp * re + ex) & 31);
+        }
+        n += __popc(ball);
+    }
+    __syncwarp();
+    const int start = p.out.unit_start[warp], end = p.out.unit_start[warp + 1];
+    for (int s = start + lane; s < end; s += 32)
+        if (s < p.capacity) { p.out.slot_pix[s] = -1; p.out.slot_rc[s] = -1; }
+    __syncwarp();
+    if (n == 0) return;
+    // 2. counting sort by bank: lane = bank value; stable in row-major order
+    int cnt = 0;
+    for (int t = 0; t < n; ++t) cnt += s_h[wib][t] == lane;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    int rank = incl - cnt;
+    // 3. rank -> position: ranks laid out in kSpreadRows rows of m, read column by column, dealt to the
+    //    4-slot groups round-robin (position = 4 * group + index in group)
+    const int m = (n + kSpreadRows - 1) / kSpreadRows, nfull = n / m, part = n % m;
+    const int gtot = ((n + 3) & ~3) / 4;
+    for (int t = 0; t < n; ++t) {
+        if (s_h[wib][t] != lane) continue;
+        const int rr = rank / m, cc = rank % m;
+        const int f = cc * nfull + (cc < part ? cc : part) + rr;
+        const int slot = start + 4 * (f % gtot) + f / gtot;
+        ++rank;
+        if (slot < p.capacity) {
+            p.out.slot_pix[slot] = s_pix[wib][t];
+            p.out.slot_rc[slot] = s_rc[wib][t];
+            p.out.slot_map[s_pix[wib][t]] = slot;
+        } else {
+            p.out.slot_map[s_pix[wib][t]] = -1;
+        }
+    }
+}
+
 // Single block: exclusive scan of the padded unit counts.
 __global__ void __launch_bounds__(1024) plane_units_scan_kernel(PlaneListParams p) {
     __shared__ int warp_tot[32];

@@ -66,7 +66,7 @@ inline PlaneGeom geom_for(int B, int H, int W) {
 // mask (or flat edge list when mask == NULL) -> unit lists
 inline int launch_plane_lists(const float* mask, int mask_channels, int stride, const int32_t* edges,
                               const int32_t* n_edges_dev, int max_edges, const PlaneGeom& g, int cap, void* ws,
-                              cudaStream_t st) {
+                              cudaStream_t st, int srp = 17) {
     const PlaneListsLayout lay = plane_lists_layout(g, cap);
     PlaneListParams p{};
     p.mask = mask; p.mask_channels = mask_channels; p.stride = stride;
@@ -82,7 +82,7 @@ inline int launch_plane_lists(const float* mask, int mask_channels, int stride, 
     const int blocks = (g.n_units * 32 + 255) / 256;
     plane_units_kernel<0><<<blocks, 256, 0, st>>>(p);
     plane_units_scan_kernel<<<1, 1024, 0, st>>>(p);
-    plane_units_kernel<1><<<blocks, 256, 0, st>>>(p);
+    plane_units_emit_kernel<<<(g.n_units + 7) / 8, 256, 0, st>>>(p, srp);
     return check_launch("plane_lists", 5);
 }
 
@@ -216,7 +216,7 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
     const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, loss_blocks, grad_sr != nullptr);
     SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
     char* ws = static_cast<char*>(workspace);
-    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st)) return e;
+    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st, Cfg::SRP)) return e;
     const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
     float* q_sr = reinterpret_cast<float*>(ws + l.off_q[0]);
     float* q_gt = reinterpret_cast<float*>(ws + l.off_q[1]);
@@ -255,7 +255,7 @@ inline int launch_plane_rows_backward_cfg(const void* img, int dtype, int B, int
     const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, 2 * di.sm_count, true);
     SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
     char* ws = static_cast<char*>(workspace);
-    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st)) return e;
+    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st, Cfg::SRP)) return e;
     const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
     float* gqT = reinterpret_cast<float*>(ws + l.off_q[0]);
     float* gcls = reinterpret_cast<float*>(ws + l.off_gcls);

@@ -293,7 +293,7 @@ extern "C" int ssl_b200_plane_rows_forward(const void* image, const void* image2
         const PlaneFwdLayout l = plane_fwd_layout<Cfg>(B, H, W, max_edges);
         SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
         char* ws = static_cast<char*>(workspace);
-        if (int e = launch_plane_lists(nullptr, 1, 0, edges, n_edges_dev, max_edges, l.g, l.cap, ws, st)) return e;
+        if (int e = launch_plane_lists(nullptr, 1, 0, edges, n_edges_dev, max_edges, l.g, l.cap, ws, st, Cfg::SRP)) return e;
         const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
         float* q0 = reinterpret_cast<float*>(ws + l.off_q[0]);
         float* q1 = image2 ? reinterpret_cast<float*>(ws + l.off_q[1]) : nullptr;
