@@ -321,13 +321,31 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
                         for (int a = -K; a <= K; ++a) v[e][a + K] = sp[a * Cfg::SRP];
                     }
                     float out[4];
+                    if (ca == K) {
+                        // unclipped dy (17 of 25): all 2K+1 rows, summed pairwise (short dependency chains)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float acc = 0.f;
+                        for (int e = 0; e < 4; ++e) {
+                            float t[2 * K + 1];
 #pragma unroll
-                        for (int a = -K; a <= K; ++a)
-                            if (a >= alo && a <= ahi) acc += v[e][a + K];
-                        out[e] = rcs[e] >= 0 ? acc + eo[e] : 0.f;
+                            for (int a = 0; a < 2 * K + 1; ++a) t[a] = v[e][a];
+#pragma unroll
+                            for (int w = 1; w < 2 * K + 1; w *= 2)
+#pragma unroll
+                                for (int a = 0; a + w < 2 * K + 1; a += 2 * w) t[a] += t[a + w];
+                            out[e] = rcs[e] >= 0 ? t[0] + eo[e] : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t[2 * K + 1];
+#pragma unroll
+                            for (int a = -K; a <= K; ++a) t[a + K] = (a >= alo && a <= ahi) ? v[e][a + K] : 0.f;
+#pragma unroll
+                            for (int w = 1; w < 2 * K + 1; w *= 2)
+#pragma unroll
+                                for (int a = 0; a + w < 2 * K + 1; a += 2 * w) t[a] += t[a + w];
+                            out[e] = rcs[e] >= 0 ? t[0] + eo[e] : 0.f;
+                        }
                     }
                     *reinterpret_cast<float4*>(qT + qrow + gs) = make_float4(out[0], out[1], out[2], out[3]);
                 }
