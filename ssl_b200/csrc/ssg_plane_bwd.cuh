@@ -138,17 +138,41 @@ __device__ __forceinline__ void place_fetch(const PlaneBwdParams& p, const int32
     }
 }
 
-template <typename Cfg>
-__device__ __forceinline__ int place_entry(float* ucol, int packed, float val, int lo_off, int hi_off) {
-    if (packed < 0) return 0;
-    const int rr = packed & 255;
-    int r0 = rr + lo_off, r1 = rr + hi_off;
-    r0 = r0 < 0 ? 0 : r0;
-    r1 = r1 > Cfg::ROWS - 1 ? Cfg::ROWS - 1 : r1;
-    if (r0 > r1) return 0;
-    ucol[r0] += val;
-    ucol[r1 + 1] -= val;
-    return 1;
+// Enter NB edge pixels of ONE kind into the column.  Entries of a kind have distinct rows, so the NB "+val"
+// addresses are distinct, and so are the NB "-val" addresses: each half is done as NB independent loads,
+// NB adds, NB stores (two dependent shared-memory round trips per batch instead of 2*NB).  The two clamped
+// cases are kept out of shared memory: runs starting above the tile add into `head` (row 0, applied once),
+// runs ending below it need no "-val" at all (nothing reads past the last row).
+template <typename Cfg, int NB>
+__device__ __forceinline__ int place_batch(float* ucol, const int (&packed)[NB], const float (&val)[NB], int lo_off,
+                                           int hi_off, float& head) {
+    int r0[NB], r1[NB], n = 0;
+    bool ok[NB];
+    float cur[NB];
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int rr = packed[m] & 255;
+        r0[m] = rr + lo_off;
+        r1[m] = rr + hi_off;
+        ok[m] = packed[m] >= 0 && r1[m] >= 0 && r0[m] <= Cfg::ROWS - 1;
+        n += ok[m];
+    }
+#pragma unroll
+    for (int m = 0; m < NB; ++m)
+        if (ok[m] && r0[m] > 0) cur[m] = ucol[r0[m]];
+#pragma unroll
+    for (int m = 0; m < NB; ++m)
+        if (ok[m]) {
+            if (r0[m] > 0) ucol[r0[m]] = cur[m] + val[m];
+            else head += val[m];
+        }
+#pragma unroll
+    for (int m = 0; m < NB; ++m)
+        if (ok[m] && r1[m] < Cfg::ROWS - 1) cur[m] = ucol[r1[m] + 1];
+#pragma unroll
+    for (int m = 0; m < NB; ++m)
+        if (ok[m] && r1[m] < Cfg::ROWS - 1) ucol[r1[m] + 1] = cur[m] - val[m];
+    return n;
 }
 
 template <typename Cfg, int NB>
@@ -158,11 +182,10 @@ __device__ __forceinline__ void place_apply(const int32_t* ent, float* ucol, con
 #pragma unroll
     for (int i = 0; i < BC::U_COL / 4; ++i) ucol4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     int n_items = 0;
+    float head = 0.f;
 #pragma unroll
     for (int kind = 0; kind < 2; ++kind) {
-#pragma unroll
-        for (int m = 0; m < NB; ++m)
-            n_items += place_entry<Cfg>(ucol, f.packed[kind][m], f.val[kind][m], f.lo_off[kind], f.hi_off[kind]);
+        n_items += place_batch<Cfg, NB>(ucol, f.packed[kind], f.val[kind], f.lo_off[kind], f.hi_off[kind], head);
         // columns with more than NB entries of a kind (dense masks): the rest, in batches of 4
         for (int e = f.e0[kind] + NB; e < f.e1[kind]; e += 4) {
             int packed[4];
@@ -172,16 +195,17 @@ __device__ __forceinline__ void place_apply(const int32_t* ent, float* ucol, con
                 packed[m] = e + m < f.e1[kind] ? ent[e + m] : -1;
                 val[m] = packed[m] >= 0 ? __ldg(f.gq[kind] + (packed[m] >> 8)) : 0.f;
             }
-#pragma unroll
-            for (int m = 0; m < 4; ++m) n_items += place_entry<Cfg>(ucol, packed[m], val[m], f.lo_off[kind], f.hi_off[kind]);
+            n_items += place_batch<Cfg, 4>(ucol, packed, val, f.lo_off[kind], f.hi_off[kind], head);
         }
     }
     if (n_items == 0) return;  // column stays exactly zero
-    float run = 0.f;
+    // in-place prefix sum; the four partial sums of a float4 do not wait for the running total
+    float run = head;
 #pragma unroll
     for (int i = 0; i < Cfg::ROWS / 4; ++i) {
         float4 v = ucol4[i];
-        v.x += run; v.y += v.x; v.z += v.y; v.w += v.z;
+        const float s01 = v.x + v.y, s012 = s01 + v.z, s0123 = s012 + v.w;
+        v.x += run; v.y = s01 + run; v.z = s012 + run; v.w = s0123 + run;
         run = v.w;
         ucol4[i] = v;
     }
