@@ -20,7 +20,7 @@ namespace sslb {
 // ROWS = image rows one worker covers (its threads), G = consecutive dx per sweep thread, NWP = workers
 // per CTA (worker w takes dy = w, w+NWP, ...).  The forward uses (64, 5, 5): it needs a halo of K rows
 // on each side, so tall workers waste less; the backward has no row halo and uses (32, 4, 13).
-template <int KS_, int KW_, int ROWS_ = 64, int G_ = 5, int NWP_ = 5>
+template <int KS_, int KW_, int ROWS_ = 64, int G_ = 5, int NWP_ = 5, int TX_ = 64>
 struct PlaneCfg {
     static constexpr int KS = KS_, KW = KW_;
     static constexpr int P = KS / 2, K = KW / 2;
@@ -34,7 +34,7 @@ struct PlaneCfg {
     static constexpr int NCLS = 2 * K + 1; // clip classes per axis
     // forward tiles (unpadded image coordinates of the edge pixels they own)
     static constexpr int TYF = ROWS - 2 * K;
-    static constexpr int TXF = 64;
+    static constexpr int TXF = TX_;        // tile width (a multiple of the 8-column chunk)
     static constexpr int CH = 8;           // columns per sweep chunk
     static constexpr int UNITS_X = TXF / CH;
     static constexpr int SWEEP = TXF + CH;   // one chunk of halo: 2K <= CH columns
@@ -56,7 +56,7 @@ struct PlaneCfg {
 
 // Backward geometry that goes with a forward configuration.
 template <typename Cfg>
-using PlaneBwdGeom = PlaneCfg<Cfg::KS, Cfg::KW, 32, 4, 13>;
+using PlaneBwdGeom = PlaneCfg<Cfg::KS, Cfg::KW, 32, 4, 13, 96>;
 
 // in-area range of window offsets for search offset t, per axis
 __host__ __device__ constexpr int rng_lo(int t, int P, int K) { return -P - t > -K ? -P - t : -K; }

@@ -285,6 +285,8 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
             sweep_chunk_bwd<Cfg, GI>(tile, uworker, r, dy, k, carry, acc);
             // 3. add into the accumulator tile (output chunk k-1) when it is this worker's turn
             if (k >= 1) {
+                // (flag-based hand-over: compute-sanitizer's racecheck, which only knows barriers, reports the
+                //  accumulator updates below as hazards; the fences + the volatile ticket order them)
                 if (r == 0)
                     while (turn[k - 1] != ticket) __nanosleep(32);
                 worker_sync<Cfg::ROWS>(wp);
