@@ -32,14 +32,19 @@ constexpr int kRowTPhases = kRowTThreads / kRowTSlots;
 
 __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams p) {
     extern __shared__ float rl_smem[];
-    constexpr int NS = kRowTSlots;
+    constexpr int NS = kRowTSlots, NPH = kRowTPhases;
+    const int L = p.L, cap = p.cap, mode = p.mode;
     float* es = rl_smem;                // [L][NS]
-    float* et = es + p.L * NS;          // [L][NS]
-    __shared__ float red[2][kRowTPhases][NS];
+    float* et = es + L * NS;            // [L][NS]
+    __shared__ float red[2][NPH][NS];
     __shared__ double dred[32];
     const int s = threadIdx.x % NS, ph = threadIdx.x / NS;
-    const int n_slots = min(p.counts[0], p.cap);
+    const int n_slots = min(p.counts[0], cap);
     const float nscale = -1.0f / (p.denom * p.sigma);
+    const float w_l1 = p.w_l1, w_kl = p.w_kl, chain = p.chain, eps = p.eps;
+    const long long gstride = (long long)NPH * cap;   // global stride between this thread's offsets
+    constexpr int sstride = NPH * NS;                 // shared stride
+    const int n_mine = (L - ph + NPH - 1) / NPH;      // offsets d = ph, ph + NPH, ... handled by this thread
     double l1_tot = 0.0, kl_tot = 0.0;
     for (int slot0 = blockIdx.x * NS; slot0 < n_slots; slot0 += gridDim.x * NS) {
         const int slot = slot0 + s;
@@ -48,90 +53,109 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
         // of 2*UN so that enough bytes are in flight to cover the HBM latency.
         float zs = 0.f, zt = 0.f;
         constexpr int UN = 8;
-        for (int d0 = ph; d0 < p.L; d0 += kRowTPhases * UN) {
-            float qa[UN], qb[UN];
+        {
+            const float* gs = p.qs + (long long)ph * cap + slot;
+            const float* gg = p.qg + (long long)ph * cap + slot;
+            float* ps = es + ph * NS + s;
+            float* pt = et + ph * NS + s;
+            for (int i0 = 0; i0 < n_mine; i0 += UN) {
+                float qa[UN], qb[UN];
 #pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const int d = d0 + u * kRowTPhases;
-                const bool ok = valid && d < p.L;
-                qa[u] = ok ? __ldcs(p.qs + (long long)d * p.cap + slot) : 0.f;
-                qb[u] = ok ? __ldcs(p.qg + (long long)d * p.cap + slot) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const int d = d0 + u * kRowTPhases;
-                if (d < p.L) {
-                    // exp(-1 * (q / (C kw^2)) / sigma) of loss_util.py:224-225; the two divisions are folded
-                    // into one multiplication (<= 1.5 ulp of the argument, the size of q's own rounding)
-                    const float a = valid ? expf(qa[u] * nscale) : 0.f;
-                    const float b = valid ? expf(qb[u] * nscale) : 0.f;
-                    es[d * NS + s] = a;
-                    et[d * NS + s] = b;
-                    zs += a;
-                    zt += b;
+                for (int u = 0; u < UN; ++u) {
+                    const bool ok = valid && i0 + u < n_mine;
+                    qa[u] = ok ? __ldcs(gs + u * gstride) : 0.f;
+                    qb[u] = ok ? __ldcs(gg + u * gstride) : 0.f;
                 }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    if (i0 + u < n_mine) {
+                        // exp(-1 * (q / (C kw^2)) / sigma) of loss_util.py:224-225; the two divisions are folded
+                        // into one multiplication (<= 1.5 ulp of the argument, the size of q's own rounding)
+                        const float a = valid ? expf(qa[u] * nscale) : 0.f;
+                        const float b = valid ? expf(qb[u] * nscale) : 0.f;
+                        ps[u * sstride] = a;
+                        pt[u * sstride] = b;
+                        zs += a;
+                        zt += b;
+                    }
+                }
+                gs += UN * gstride; gg += UN * gstride;
+                ps += UN * sstride; pt += UN * sstride;
             }
         }
         red[0][ph][s] = zs;
         red[1][ph][s] = zt;
         __syncthreads();
         float rs = 1.f, rt = 1.f;
-        if (p.mode == SSL_B200_ROWS_NORM) {
+        if (mode == SSL_B200_ROWS_NORM) {
             float a = 0.f, b = 0.f;
 #pragma unroll
-            for (int k = 0; k < kRowTPhases; ++k) { a += red[0][k][s]; b += red[1][k][s]; }
-            rs = 1.0f / (a + p.eps);
-            rt = 1.0f / (b + p.eps);
+            for (int k = 0; k < NPH; ++k) { a += red[0][k][s]; b += red[1][k][s]; }
+            rs = 1.0f / (a + eps);
+            rt = 1.0f / (b + eps);
         }
         __syncthreads();
         // pass 2: rows, loss terms, dL/drow; es <- s, et <- g
         float l1 = 0.f, kl = 0.f, dot = 0.f;
-        for (int d = ph; d < p.L; d += kRowTPhases) {
-            const float sv = rs * es[d * NS + s], tv = rt * et[d * NS + s];
-            const float df = sv - tv;
-            l1 += fabsf(df);
-            float g = p.w_l1 * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
-            if (p.w_kl != 0.f) {
-                const float sc = fmaxf(sv, 1e-10f), tc = fmaxf(tv, 1e-10f);
-                kl += kl_term(sc, tc) + (p.mode == SSL_B200_ROWS_NORM ? ((tc - tv) - (sc - sv)) : (tc - sc));
-                if (sv > 1e-10f) g -= p.w_kl * tc / sc;
+        {
+            float* ps = es + ph * NS + s;
+            float* pt = et + ph * NS + s;
+            for (int i = 0; i < n_mine; ++i, ps += sstride, pt += sstride) {
+                const float sv = rs * *ps, tv = rt * *pt;
+                const float df = sv - tv;
+                l1 += fabsf(df);
+                float g = df > 0.f ? w_l1 : (df < 0.f ? -w_l1 : 0.f);
+                if (w_kl != 0.f) {
+                    const float sc = fmaxf(sv, 1e-10f), tc = fmaxf(tv, 1e-10f);
+                    kl += kl_term(sc, tc) + (mode == SSL_B200_ROWS_NORM ? ((tc - tv) - (sc - sv)) : (tc - sc));
+                    if (sv > 1e-10f) g -= w_kl * tc / sc;
+                }
+                if (!valid) g = 0.f;
+                dot = fmaf(g, sv, dot);
+                *ps = sv;
+                *pt = g;
             }
-            if (!valid) g = 0.f;
-            dot = fmaf(g, sv, dot);
-            es[d * NS + s] = sv;
-            et[d * NS + s] = g;
         }
         if (valid) { l1_tot += (double)l1; kl_tot += (double)kl; }
         if (p.want_grad) {
             red[0][ph][s] = dot;
             __syncthreads();
             float dsum = 0.f;
-            if (p.mode == SSL_B200_ROWS_NORM) {
+            if (mode == SSL_B200_ROWS_NORM) {
 #pragma unroll
-                for (int k = 0; k < kRowTPhases; ++k) dsum += red[0][k][s];
+                for (int k = 0; k < NPH; ++k) dsum += red[0][k][s];
             }
             // pass 3: dL/dq = chain * s * (g - sum_m g_m s_m)   (EXP rows: chain * e * g)
-            for (int d = ph; d < p.L; d += kRowTPhases) {
-                const float gq = p.chain * es[d * NS + s] * (et[d * NS + s] - dsum);
-                es[d * NS + s] = gq;
-                if (slot < n_slots) p.qs[(long long)d * p.cap + slot] = gq;
+            {
+                float* ps = es + ph * NS + s;
+                const float* pt = et + ph * NS + s;
+                float* gs = p.qs + (long long)ph * cap + slot;
+                const bool store = slot < n_slots;
+                for (int i = 0; i < n_mine; ++i, ps += sstride, pt += sstride, gs += gstride) {
+                    const float gq = chain * *ps * (*pt - dsum);
+                    *ps = gq;
+                    if (store) *gs = gq;
+                }
             }
             __syncthreads();
             // pass 4: per clip class sums of dL/dq (classes with nothing out of area are skipped)
             if (p.gcls && slot < n_slots) {
-                const int NC = 2 * p.K + 1, U = p.P - p.K;
-                for (int c = ph; c < NC * NC; c += kRowTPhases) {
+                const int K = p.K, P = p.P, KS = p.KS;
+                const int NC = 2 * K + 1, U = P - K;
+                for (int c = ph; c < NC * NC; c += NPH) {
                     const int ca = c / NC, cb = c % NC;
                     float acc = 0.f;
-                    if (ca != p.K || cb != p.K) {
-                        const int dy0 = ca < p.K ? ca - p.P : (ca > p.K ? U + (ca - p.K) : -U);
-                        const int dy1 = ca == p.K ? U : dy0;
-                        const int dx0 = cb < p.K ? cb - p.P : (cb > p.K ? U + (cb - p.K) : -U);
-                        const int dx1 = cb == p.K ? U : dx0;
-                        for (int dy = dy0; dy <= dy1; ++dy)
-                            for (int dx = dx0; dx <= dx1; ++dx) acc += es[((dy + p.P) * p.KS + dx + p.P) * NS + s];
+                    if (ca != K || cb != K) {
+                        const int dy0 = ca < K ? ca - P : (ca > K ? U + (ca - K) : -U);
+                        const int dy1 = ca == K ? U : dy0;
+                        const int dx0 = cb < K ? cb - P : (cb > K ? U + (cb - K) : -U);
+                        const int dx1 = cb == K ? U : dx0;
+                        for (int dy = dy0; dy <= dy1; ++dy) {
+                            const float* row = es + ((dy + P) * KS + dx0 + P) * NS + s;
+                            for (int dx = dx0; dx <= dx1; ++dx, row += NS) acc += *row;
+                        }
                     }
-                    p.gcls[(long long)c * p.cap + slot] = acc;
+                    p.gcls[(long long)c * cap + slot] = acc;
                 }
             }
         }
