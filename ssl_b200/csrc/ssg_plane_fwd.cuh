@@ -31,11 +31,13 @@ struct PlaneFwdParams {
 
 // ---- Eout tables -------------------------------------------------------------------------
 // eout[slot][ca*NCLS+cb] = sum over window offsets (a,b) outside A(ca) x A(cb) of sum_c I(p+(a,b))^2.
-// One warp per slot; all sums are over non-negative terms.
+// One warp per slot.  The complement of a clip range is a prefix or a suffix of the window, so every
+// entry is a sum of at most two running sums (all terms non-negative, no subtraction).
 template <typename T, typename Cfg>
 __global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
     constexpr int K = Cfg::K, KW = Cfg::KW, NC = Cfg::NCLS, NW = KW * KW;
-    __shared__ float sE[4][NW], sRout[4][KW * NC], sRfull[4][KW];
+    // sOut[a][m]: sum of the first m (m <= K) window columns of row a; sOut[a][K+1+m]: of the last m; sFull[a]: all
+    __shared__ float sE[4][NW], sPre[4][KW][K + 1], sSuf[4][KW][K + 1], sFull[4][KW];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_slots = min(p.lists.counts[0], p.cap);
     const int H = p.g.H, W = p.g.W;
@@ -60,26 +62,42 @@ __global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
             sE[w][i] = e;
         }
         __syncwarp();
-        for (int i = lane; i < KW * NC; i += 32) {
-            const int a = i / NC, cb = i % NC;
-            const int lo = class_lo(cb, K), hi = class_hi(cb, K);
-            float s = 0.f;
-            for (int bb = -K; bb <= K; ++bb)
-                if (bb < lo || bb > hi) s += sE[w][a * KW + bb + K];
-            sRout[w][i] = s;
-        }
-        if (lane < KW) {
-            float s = 0.f;
-            for (int bb = 0; bb < KW; ++bb) s += sE[w][lane * KW + bb];
-            sRfull[w][lane] = s;
+        if (lane < KW) {  // one window row per lane: running sums from the left and from the right
+            const float* row = &sE[w][lane * KW];
+            float pre = 0.f, suf = 0.f, full = 0.f;
+            sPre[w][lane][0] = 0.f;
+            sSuf[w][lane][0] = 0.f;
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+                pre += row[m];
+                suf += row[KW - 1 - m];
+                sPre[w][lane][m + 1] = pre;
+                sSuf[w][lane][m + 1] = suf;
+            }
+#pragma unroll
+            for (int m = 0; m < KW; ++m) full += row[m];
+            sFull[w][lane] = full;
         }
         __syncwarp();
-        for (int i = lane; i < NC * NC; i += 32) {
-            const int ca = i / NC, cb = i % NC;
-            const int lo = class_lo(ca, K), hi = class_hi(ca, K);
-            float s = 0.f;
-            for (int a = -K; a <= K; ++a) s += (a < lo || a > hi) ? sRfull[w][a + K] : sRout[w][(a + K) * NC + cb];
-            out[i] = s;
+        if (lane < NC) {  // one column class per lane
+            const int cb = lane;
+            // r[a] = sum over the columns of row a that are out of area for class cb
+            float r[KW], f[KW];
+#pragma unroll
+            for (int a = 0; a < KW; ++a) {
+                r[a] = cb < K ? sPre[w][a][K - cb] : (cb > K ? sSuf[w][a][cb - K] : 0.f);
+                f[a] = sFull[w][a];
+            }
+            // row classes: rows out of area are the first (ca < K) or the last (ca > K) few; they count in full,
+            // the others only with their out-of-area columns
+#pragma unroll
+            for (int ca = 0; ca < NC; ++ca) {
+                const int n_top = ca < K ? K - ca : 0, n_bot = ca > K ? ca - K : 0;
+                float s = 0.f;
+#pragma unroll
+                for (int a = 0; a < KW; ++a) s += (a < n_top || a >= KW - n_bot) ? f[a] : r[a];
+                out[ca * NC + cb] = s;
+            }
         }
         __syncwarp();
     }
