@@ -145,43 +145,23 @@ __device__ __forceinline__ void decode_unit(const PlaneGeom& g, int u, int& b, i
     b = u / g.nty;
 }
 
-// One warp per unit.  Pass 0 counts, pass 1 emits (after the scan).  The unit is walked row by row,
-// 8 columns x 4 rows per warp step, so ballot order == row-major order inside the unit.
-template <int PASS>
-__global__ void __launch_bounds__(256) plane_units_kernel(PlaneListParams p) {
+// Count pass, one warp per unit: the unit is walked 8 columns x 4 rows per warp step.
+__global__ void __launch_bounds__(256) plane_units_count_kernel(PlaneListParams p) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= p.g.n_units) return;
     int b, ty, tx, cx;
     decode_unit(p.g, warp, b, ty, tx, cx);
     const int y0 = ty * p.g.TYF, x0 = tx * p.g.TXF + cx * 8;
     const int ly = lane >> 3, lx = lane & 7;
-    int running = PASS ? p.out.unit_start[warp] : 0;
-    const int base = running;
+    int n = 0;
     for (int yy = 0; yy < p.g.TYF; yy += 4) {
         const int y = y0 + yy + ly, x = x0 + lx;
         const bool e = (yy + ly) < p.g.TYF && y < p.g.H && x < p.g.W && unit_is_edge(p, b, y, x);
-        const unsigned ball = __ballot_sync(0xffffffffu, e);
-        if (PASS && e) {
-            const int slot = running + __popc(ball & ((1u << lane) - 1u));
-            if (slot < p.capacity) {
-                p.out.slot_pix[slot] = (b * p.g.H + y) * p.g.W + x;
-                p.out.slot_rc[slot] = ((yy + ly + p.g.K) << 8) | (cx * 8 + lx);
-                p.out.slot_map[(b * p.g.H + y) * p.g.W + x] = slot;
-            }
-        }
-        running += __popc(ball);
+        n += __popc(__ballot_sync(0xffffffffu, e));
     }
-    if (PASS == 0) {
-        if (lane == 0) {
-            p.unit_count[warp] = (running + 3) & ~3;
-            if (running) atomicAdd(p.out.counts + 1, running);
-        }
-    } else {
-        // padding slots of this unit
-        const int end = p.out.unit_start[warp + 1];
-        for (int s = running + lane; s < end; s += 32)
-            if (s < p.capacity) { p.out.slot_pix[s] = -1; p.out.slot_rc[s] = -1; }
-        (void)base;
+    if (lane == 0) {
+        p.unit_count[warp] = (n + 3) & ~3;   // padded to whole float4 groups
+        if (n) atomicAdd(p.out.counts + 1, n);
     }
 }
 

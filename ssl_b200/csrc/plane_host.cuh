@@ -80,7 +80,7 @@ inline int launch_plane_lists(const float* mask, int mask_channels, int stride, 
     fill_i32_kernel<<<fill_blocks, 256, 0, st>>>(p.out.slot_map, npx, -1);
     if (!mask && max_edges > 0) plane_mark_edges_kernel<<<(max_edges + 255) / 256 < 2048 ? (max_edges + 255) / 256 : 2048, 256, 0, st>>>(p);
     const int blocks = (g.n_units * 32 + 255) / 256;
-    plane_units_kernel<0><<<blocks, 256, 0, st>>>(p);
+    plane_units_count_kernel<<<blocks, 256, 0, st>>>(p);
     plane_units_scan_kernel<<<1, 1024, 0, st>>>(p);
     plane_units_emit_kernel<<<(g.n_units + 7) / 8, 256, 0, st>>>(p, srp);
     return check_launch("plane_lists", 5);
