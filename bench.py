@@ -21,7 +21,14 @@ Reported on ONE JSON line (rank 0):
              peak (MEASURED_PEAKS.json)
   cpu_baseline  the oracle's restatement of the reference ssl_pytorch (oracle/ssl_oracle.py) timed on
              this box's host cores on a bounded sample of the same workload
-`--impl reference` times that CPU restatement as the whole run (rank 0 only).
+  gpu_baseline  the reference's own CUDA operator (similarity.cu, compiled unmodified by oracle/build_ref.py
+             into oracle/_ref) timed on this GPU on the same batch, per image as the reference does
+             (similaritywrapper.py:25-69): fwd(SR) + fwd(GT) + bwd -- the GPU bar to beat (rank 0, N=1)
+  config3    BASELINE configs[2] measured in the same run: ONE batch of 64 bf16 crops (seed 2) sharded over
+             the N ranks by ssl_b200.dist.shard_range, parity="global" (24-byte all-reduce inside the timed
+             step) -- strong scaling; its loss is checked against the fp64 oracle value of the whole batch
+The loss of every timed workload is asserted against tests/golden/bench_loss.json (fp64 oracle, 1e-5).
+`--impl reference` times the CPU restatement as the whole run (rank 0 only).
 """
 from __future__ import annotations
 
@@ -133,9 +140,23 @@ class ClockSampler:
 # CPU arm: the oracle's restatement of the reference ssl_pytorch
 # ---------------------------------------------------------------------------------------------
 
-def cpu_sample(n_px, seed=1):
-    """A bounded sample of the workload: the first crop of the config-2 batch, with the mask cut to
-    the first row bands that hold ~n_px edge pixels."""
+CPU_SAMPLE_PX = 4096   # >= 4,096 edge pixels, fixed (never resized from a cold call)
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_sample(n_px=CPU_SAMPLE_PX, seed=1):
+    """THE bounded sample of the workload, the same for cpu_baseline and --impl reference: crop 0 of the
+    config-2 batch (seed 1), mask cut to the first row bands that hold >= n_px edge pixels."""
     import torch
     from ssl_b200 import synth
     sr, gt, mask = synth.make_case(1, HEIGHT, WIDTH, seed=seed, density=DENSITY)
@@ -153,20 +174,23 @@ def cpu_step(sr, gt, mask):
     return time.perf_counter() - t0, n
 
 
-def cpu_baseline(budget_s=15.0):
-    """Edge-px/s of the CPU restatement on ~budget_s seconds of work."""
+def cpu_sample_text(n):
+    return (f"{n} edge px = crop 0 of the workload (seed 1) cut to its first row bands holding >= {CPU_SAMPLE_PX} "
+            f"edge px; fwd(SR)+fwd(GT)+L1+bwd with oracle.ssl_step_pytorch_port (op-for-op restatement of the "
+            f"reference ssl_pytorch, 512-px chunks; the reference itself is Python under /root/reference and does "
+            f"not travel to the GPU box); full-batch figures are a linear extrapolation")
+
+
+def cpu_baseline():
+    """Edge-px/s of the CPU restatement on the fixed sample: one warm-up call, then the best of 3."""
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    sr, gt, m, n = cpu_sample(256)
-    dt, _ = cpu_step(sr, gt, m)          # warm-up + calibration
-    rate = n / dt
-    n_px = int(min(max(rate * budget_s, 256), 16384))
-    sr, gt, m, n = cpu_sample(n_px)
-    dt, _ = cpu_step(sr, gt, m)
-    return {"value": n / dt, "unit": "edge-pixels/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} edge px of crop 0 of the workload (first row bands), fwd(SR)+fwd(GT)+L1+bwd with "
-                      f"oracle.ssl_step_pytorch_port (restated ssl_pytorch, 512-px chunks), {dt:.1f} s wall, "
-                      f"{os.cpu_count()} host cpus"}
+    sr, gt, m, n = cpu_sample()
+    cpu_step(sr, gt, m)
+    times = [cpu_step(sr, gt, m)[0] for _ in range(3)]
+    return {"value": n / min(times), "unit": "edge-pixels/s", "cores": torch.get_num_threads(), "kind": "port",
+            "cpu_model": cpu_model(), "host_cpus": os.cpu_count(), "best_of": 3,
+            "times_s": [round(t, 3) for t in times], "sample": cpu_sample_text(n)}
 
 
 def run_reference(args):
@@ -175,36 +199,98 @@ def run_reference(args):
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    sr, gt, m, n = cpu_sample(128)
-    dt, _ = cpu_step(sr, gt, m)
-    rate = n / dt
-    total_steps = args.steps + args.warmup
-    n_px = int(min(max(rate * 120.0 / max(total_steps, 1), 64), 4096))
-    sr, gt, m, n = cpu_sample(n_px)
+    sr, gt, m, n = cpu_sample()
     for _ in range(args.warmup):
         cpu_step(sr, gt, m)
-    t = 0.0
-    for _ in range(args.steps):
-        dt, _ = cpu_step(sr, gt, m)
-        t += dt
+    times = [cpu_step(sr, gt, m)[0] for _ in range(args.steps)]
+    t = sum(times)
     value = n * args.steps / t
-    sample = (f"each step = {n} edge px of crop 0 of the workload (first row bands), fwd(SR)+fwd(GT)+L1+bwd, "
-              f"oracle.ssl_step_pytorch_port (op-for-op restatement of the reference ssl_pytorch; the reference "
-              f"itself is Python under /root/reference and does not travel to the GPU box)")
     out = {"impl": "reference", "metric": baseline_metric(), "value": value, "unit": "edge-pixels/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": workload_config(args.gpus),
            "cpu_baseline": {"value": value, "unit": "edge-pixels/s", "cores": torch.get_num_threads(),
-                            "kind": "port", "sample": sample},
+                            "kind": "port", "cpu_model": cpu_model(), "host_cpus": os.cpu_count(),
+                            "best_step_value": n / min(times), "sample": "each step = " + cpu_sample_text(n)},
            "e2e": {"value": value, "unit": "edge-pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
+# GPU baseline-to-beat: the reference's own similarity.cu on the same device
+# ---------------------------------------------------------------------------------------------
+
+def gpu_baseline(sr_d, gt_d, mask_h, n_edges, steps=3):
+    """Times oracle/_ref/libsimilarity_ref.so (the reference's unmodified CUDA op) on the batch the B200
+    arm just processed, the way the reference drives it: per image, fwd(SR) + fwd(GT) into zero-filled
+    outputs and one backward into a zero-filled padded gradient (similaritywrapper.py:25-57).  Padding,
+    `nonzero` and the exp / normalise / L1 tail are left OUT of the timed region (in the reference's favour).
+    The reference launches on the legacy default stream; so are the events."""
+    import torch
+    from oracle import build_ref
+    lib = build_ref.load()
+    if lib is None:
+        return {"unavailable": "oracle/_ref/libsimilarity_ref.so not built (python -m oracle.build_ref)"}
+    dev = sr_d.device
+    P = KS // 2
+    B = sr_d.shape[0]
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    pads, poss = [], []
+    for i in range(B):
+        sp = torch.nn.functional.pad(sr_d[i].float(), (P, P, P, P), mode="reflect").contiguous()
+        gp = torch.nn.functional.pad(gt_d[i].float(), (P, P, P, P), mode="reflect").contiguous()
+        mp = torch.nn.functional.pad(mask_h[i, 0].to(dev), (P, P, P, P))
+        pos = torch.nonzero(mp == 1).to(torch.int32).contiguous()
+        pads.append((sp, gp))
+        poss.append(pos)
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    grads = [(1e-6 * torch.randn(p.shape[0], L, generator=gen)).to(dev) for p in poss]
+    c, hp, wp = pads[0][0].shape
+    assert torch.cuda.current_stream().cuda_stream == 0, "gpu_baseline must run on the legacy default stream"
+
+    def one_pass():
+        for i in range(B):
+            mc = poss[i].shape[0]
+            if mc == 0:
+                continue
+            for img in pads[i]:
+                out = torch.zeros(mc, KS, KS, device=dev)
+                rc = lib.ref_compute_similarity(vp(img), vp(poss[i]), vp(out), mc, KS, KW, hp, wp, c)
+                assert rc == 0
+            gi = torch.zeros(c, hp, wp, device=dev)
+            rc = lib.ref_compute_similarity_backward(vp(pads[i][0]), vp(grads[i]), vp(poss[i]), vp(gi), mc, KS, KW,
+                                                     hp, wp, c)
+            assert rc == 0
+
+    one_pass()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one_pass()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b) * 1e-3)
+    t = min(times)
+    return {"value": n_edges / t, "unit": "edge-pixels/s", "ms_per_step": 1e3 * t, "steps": steps, "kind": "reference",
+            "what": "reference similarity.cu (unmodified, nvcc sm_100, 16-thread blocks, global fp32 atomics), per "
+                    "image: _compute_similarity(SR) + _compute_similarity(GT) + _compute_similarity_backward; "
+                    "best of %d passes over the same %d-crop batch; pad/nonzero/exp/normalise/L1 not timed" % (steps, B)}
+
+
+# ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
+
+def bench_golden():
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_loss.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
 
 def run_b200(args):
     import torch
@@ -235,8 +321,9 @@ def run_b200(args):
 
     import ssl_b200
     from ssl_b200 import _lib, synth
-    from ssl_b200 import functional as F_
+    from ssl_b200.dist import shard_range
     lib = _lib.load()
+    golden = bench_golden()
 
     def barrier():
         if world > 1:
@@ -257,17 +344,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    sr_h, gt_h, mask_h = synth.make_case(BATCH_PER_GPU, HEIGHT, WIDTH, seed=1 + rank, density=DENSITY)
-    sr_h, gt_h, mask_h = sr_h.pin_memory(), gt_h.pin_memory(), mask_h.pin_memory()
-    sr_d, gt_d, mask_d = sr_h.to(dev), gt_h.to(dev), mask_h.to(dev)
-    n_edges = int(mask_h.sum().item())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step():
-        x = sr_d.detach().requires_grad_(True)
-        loss = ssl_b200.ssl(x, gt_d, mask_d, KS, KW, SIGMA, True, EPS, loss_weight=1.0, parity="global")
-        loss.backward()
-        return loss, x.grad
 
     def timed_steps(fn, k, w):
         for _ in range(w):
@@ -283,6 +360,22 @@ def run_b200(args):
             evs.append((a, b))
         barrier()
         return sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+
+    # ---- workload (BASELINE configs[1], per rank) ------------------------------------------------
+    sr_h, gt_h, mask_h = synth.make_case(BATCH_PER_GPU, HEIGHT, WIDTH, seed=1 + rank, density=DENSITY)
+    sr_h, gt_h, mask_h = sr_h.pin_memory(), gt_h.pin_memory(), mask_h.pin_memory()
+    sr_d, gt_d, mask_d = sr_h.to(dev), gt_h.to(dev), mask_h.to(dev)
+    n_edges = int(mask_h.sum().item())
+    state = {}
+
+    def step():
+        # max_edges = rows capacity known to the caller: the whole step is enqueued without a host sync
+        x = sr_d.detach().requires_grad_(True)
+        loss = ssl_b200.ssl(x, gt_d, mask_d, KS, KW, SIGMA, True, EPS, loss_weight=1.0, parity="global",
+                            max_edges=n_edges)
+        loss.backward()
+        state["loss"], state["grad"] = loss.detach(), x.grad
+        return loss, x.grad
 
     # ---- value: inputs resident in HBM ------------------------------------------------------
     # The library brackets each of its stages with CUDA events on the launching stream while
@@ -301,6 +394,15 @@ def run_b200(args):
     total_edges = sum_over_ranks(float(n_edges))
     value = total_edges * args.steps / t_step
     total_launches = int(sum_over_ranks(float(launches)))
+    # the loss the timed step computed (global mean over all ranks' rows) against the fp64 oracle
+    loss_check = None
+    if golden is not None and all(str(1 + r) in golden["config2_fp32"] for r in range(world)):
+        num = sum(golden["config2_fp32"][str(1 + r)] * golden["config2_rows"][str(1 + r)] for r in range(world))
+        want = num / sum(golden["config2_rows"][str(1 + r)] for r in range(world))
+        got = float(state["loss"])
+        loss_check = {"loss": got, "oracle_fp64": want, "rel_err": abs(got - want) / want}
+        assert loss_check["rel_err"] <= 1e-5, f"bench.py: timed step computed loss {got}, fp64 oracle says {want}"
+        assert bool(torch.isfinite(state["grad"]).all()) and float(state["grad"].abs().max()) > 0
 
     # ---- e2e: host buffers through the C ABI --------------------------------------------------
     grad_h = torch.empty_like(sr_h).pin_memory()
@@ -309,7 +411,7 @@ def run_b200(args):
         return ssl_b200.ssl_step_host(sr_h, gt_h, mask_h, KS, KW, SIGMA, True, EPS, 1.0, out_grad=grad_h)
 
     for _ in range(max(args.warmup, 3)):
-        host_step()
+        loss_host, _, _ = host_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -322,6 +424,42 @@ def run_b200(args):
            "d2h_bytes_per_step": int(world * (grad_h.numel() * 4 + 12 + 8)),
            "ms_per_step": 1e3 * t_host / args.steps,
            "call": "ssl_b200_loss_step_host (pinned host sr/gt/mask in, loss[3] + d loss/d sr out, wall clock)"}
+    if golden is not None and str(1 + rank) in golden["config2_fp32"]:
+        want = golden["config2_fp32"][str(1 + rank)]
+        assert abs(float(loss_host[0]) - want) <= 1e-5 * want, "bench.py: host step loss disagrees with the oracle"
+
+    # ---- config 3: ONE 64-crop bf16 batch sharded over the ranks (strong scaling) ---------------
+    config3 = None
+    if not args.no_config3 and 64 % world == 0:
+        sr3, gt3, mask3 = synth.make_case(64, HEIGHT, WIDTH, seed=2, density=DENSITY)
+        idx = list(shard_range(64, rank, world))
+        sr3_d, gt3_d = sr3[idx].bfloat16().to(dev), gt3[idx].bfloat16().to(dev)
+        mask3_d = mask3[idx].to(dev)
+        n3_local, n3_total = int(mask3[idx].sum().item()), int(mask3.sum().item())
+        del sr3, gt3
+        st3 = {}
+
+        def step3():
+            x = sr3_d.detach().requires_grad_(True)
+            loss = ssl_b200.ssl(x, gt3_d, mask3_d, KS, KW, SIGMA, True, EPS, loss_weight=1.0, parity="global",
+                                max_edges=n3_local)
+            loss.backward()
+            st3["loss"], st3["grad"] = loss.detach(), x.grad
+
+        k3 = max(3, args.steps // 2)
+        t3 = max_over_ranks(timed_steps(step3, k3, 3))
+        config3 = {"workload": "configs[2]: ONE batch of 64 256x256 bf16 crops (seed 2) sharded by image over the "
+                               "ranks, fp32 arithmetic, parity=global (NCCL all-reduce of [sum|d|, sumKL, n_rows] "
+                               "inside the timed step)",
+                   "value": n3_total * k3 / t3, "unit": "edge-pixels/s", "ms_per_step": 1e3 * t3 / k3, "steps": k3,
+                   "scaling": "strong", "dtype": "bf16 storage, f32 arithmetic", "crops_per_gpu": 64 // world,
+                   "edge_px_per_step": n3_total, "loss": float(st3["loss"])}
+        if golden is not None and golden.get("config3_bf16"):
+            want = golden["config3_bf16"]["loss"]
+            config3["oracle_fp64"] = want
+            config3["rel_err"] = abs(config3["loss"] - want) / want
+            assert config3["rel_err"] <= 1e-5, f"bench.py: config-3 loss {config3['loss']} vs fp64 oracle {want}"
+        del sr3_d, gt3_d, mask3_d, st3
 
     # ---- roofline of the dominant kernel (rank 0's GPU, from the timed region's own launches) ---
     roof = None
@@ -355,18 +493,24 @@ def run_b200(args):
             except Exception:
                 pass
 
-    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()
+    # ---- baselines (rank 0, N=1 only) -----------------------------------------------------------
+    cpu = gpu_ref = None
+    if rank == 0 and world == 1:
+        if not args.no_gpu_baseline:
+            gpu_ref = gpu_baseline(sr_d, gt_d, mask_h, n_edges)
+            if "value" in gpu_ref:
+                gpu_ref["speedup_device_timed"] = value / gpu_ref["value"]
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline()
 
     if rank == 0:
         out = {"metric": baseline_metric(), "value": value, "unit": "edge-pixels/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": workload_config(world), "edge_px_per_step": int(total_edges),
-               "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
-               "gpu_launches": total_launches, "clocks": clocks.summary()}
+               "host_syncs_per_step": 0, "loss_check": loss_check,
+               "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "gpu_baseline": gpu_ref, "e2e": e2e,
+               "config3": config3, "gpu_launches": total_launches, "clocks": clocks.summary()}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -379,6 +523,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -391,7 +537,9 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
                    os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
-                   str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+                   str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + \
+                  (["--no-gpu-baseline"] if args.no_gpu_baseline else []) + \
+                  (["--no-config3"] if args.no_config3 else [])
             raise SystemExit(subprocess.call(cmd))
         run_b200(args)
 

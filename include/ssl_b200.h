@@ -153,7 +153,9 @@ int ssl_b200_plane_rows_backward(const void* image, int dtype, int B, int C, int
  *   grad_sr      fp32 [B,C,H,W] or NULL: OVERWRITTEN with d(w_l1*sum|d| + w_kl*sumKL)/d sr, i.e.
  *                the gradient before the 1/N of the 'mean' reduction (N = n_rows*ks*ks is only
  *                known once the counts of all ranks are: the caller scales)
- *   terms        double [3], OVERWRITTEN: sum|S_sr - S_gt|, sum KL, n_rows
+ *   terms        double [3], OVERWRITTEN: sum|S_sr - S_gt|, sum KL, n_rows.  If the edge list overflowed its
+ *                capacity (counts[1] > counts[0]) or holds more than max_edges pixels, n_rows is NaN, so
+ *                the loss and the gradient scale derived from it are NaN (no silent truncation)
  *   workspace    ssl_b200_loss_workspace_bytes(...) bytes of scratch (rows never leave it)
  *   path         SSL_B200_PATH_*; the same value must be given to ssl_b200_loss_workspace_bytes */
 size_t ssl_b200_loss_workspace_bytes(int B, int C, int H, int W, int ks, int kw, int max_edges, int path);
@@ -161,6 +163,13 @@ int ssl_b200_loss_forward_backward(const void* sr, const void* gt, int dtype, in
                                    const int32_t* edges, const int32_t* counts, int max_edges, int ks, int kw,
                                    float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* grad_sr,
                                    double* terms, void* workspace, size_t workspace_bytes, int path, void* stream);
+
+/* Test / inspection hook: dL/dq (the gradient with respect to the raw patch distances, before the 1/N of the
+ * 'mean') that the last ssl_b200_loss_forward_backward call with a non-NULL grad_sr left in `workspace`,
+ * copied out as fp32 rows [n, ks*ks] in the order of `edges`.  Same shape arguments as that call. */
+int ssl_b200_loss_export_distance_grad(const void* workspace, size_t workspace_bytes, int B, int C, int H, int W,
+                                       const int32_t* edges, const int32_t* counts, int max_edges, int ks, int kw,
+                                       int path, float* gq_rows, void* stream);
 
 /* Same step on HOST buffers (the end-to-end call of a host-side plugin): copies sr/gt/mask to the
  * device, builds the edge list, runs the step, applies the 'mean' (single device: N is local) and

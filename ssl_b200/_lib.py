@@ -55,6 +55,8 @@ SIGNATURES = {
                                                 _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_float,
                                                 _c_int, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p,
                                                 _c_size_t, _c_int, _c_void_p]),
+    "ssl_b200_loss_export_distance_grad": (_c_int, [_c_void_p, _c_size_t, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                                    _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "ssl_b200_loss_step_host": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                          _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_float, _c_float,
                                          _c_void_p, _c_void_p, _c_void_p, _c_void_p]),

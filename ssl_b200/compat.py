@@ -25,14 +25,22 @@ class similarity_map:  # noqa: N801  (reference spelling)
                  kernel_size_window=9, sigma=0.004, *, simself_strategy=None, kernel_size=None, scaling_factor=None,
                  kernel_size_center=None, softmax=None, **_ignored):
         eps = 1e-10  # loss_util.py:227,242
+        if ssl_mode is not None and not isinstance(ssl_mode, str):
+            # the diffusion-side constructor's third positional parameter is `img_sr` (loss_util.py:243), the GAN
+            # side's is `ssl_mode`: a tensor here means diffusion-style positional arguments, which cannot be told
+            # apart safely -- ddpmssl.py:452-467 passes everything by keyword, and so must other callers
+            raise TypeError("similarity_map: pass the diffusion-side arguments (simself_strategy, kernel_size, ...) "
+                            "by keyword; the third positional argument is ssl_mode")
         if simself_strategy is not None:  # diffusion-side keyword set (ddpmssl.py:452-467)
             if simself_strategy != _DM_STRATEGY:
                 raise ValueError(f"only simself_strategy={_DM_STRATEGY!r} (the shipped configuration) is supported, "
                                  f"got {simself_strategy!r}")
+            # defaults of the diffusion-side constructor (Diffusion-Based-SR/basicsr/losses/loss_util.py:243-247):
+            # kernel_size=5 (the shared positional default), scaling_factor=4, kernel_size_center=9, softmax=True
             kernel_size_search = kernel_size if kernel_size is not None else kernel_size_search
             kernel_size_window = kernel_size_center if kernel_size_center is not None else 9
-            sigma = scaling_factor if scaling_factor is not None else 1.0
-            generalization = bool(softmax)
+            sigma = scaling_factor if scaling_factor is not None else 4
+            generalization = True if softmax is None else bool(softmax)
             eps = 1e-20  # Diffusion-Based-SR/basicsr/losses/loss_util.py:1250
         elif ssl_mode not in _GAN_MODES:
             raise ValueError("The ssl_mode should either be cuda or pytorch.")  # loss_util.py:178-179

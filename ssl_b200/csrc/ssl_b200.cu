@@ -374,7 +374,20 @@ __global__ void __launch_bounds__(256) scale_kernel(float4* g, long long n4, con
     }
 }
 
-__global__ void set_terms_count_kernel(const int32_t* counts, double* terms) { terms[2] = (double)counts[0]; }
+// terms[2] = number of rows.  An edge list that overflowed its capacity (counts[1] = pixels found >
+// counts[0] = pixels listed) would silently drop the trailing images of the batch: poison the count instead,
+// so that the loss and the gradient scale come out NaN without any host round trip.
+__global__ void set_terms_count_kernel(const int32_t* counts, int max_edges, double* terms) {
+    const bool overflow = counts[1] > counts[0] || counts[0] > max_edges;
+    terms[2] = overflow ? __longlong_as_double(0x7ff8000000000000ll) : (double)counts[0];
+}
+
+__global__ void __launch_bounds__(256) copy_rows_kernel(const float* src, const int32_t* n_dev, int max_edges, int L,
+                                                        float* dst) {
+    const long long n = (long long)edge_count(n_dev, max_edges) * L;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
 
 }  // namespace
 
@@ -424,7 +437,7 @@ extern "C" int ssl_b200_loss_forward_backward(const void* sr, const void* gt, in
     SSLB_CUDA(cudaMemsetAsync(terms, 0, 3 * sizeof(double), st));
     const bool plane = max_edges > 0 && use_plane_path(path, B, C, H, W, ks, kw, max_edges);
     if (grad_sr && !plane) SSLB_CUDA(cudaMemsetAsync(grad_sr, 0, sizeof(float) * (size_t)B * C * H * W, st));
-    set_terms_count_kernel<<<1, 1, 0, st>>>(counts, terms);
+    set_terms_count_kernel<<<1, 1, 0, st>>>(counts, max_edges, terms);
     if (int e = check_launch("set_terms_count")) return e;
     if (max_edges <= 0) return 0;
     if (plane) {
@@ -447,6 +460,32 @@ extern "C" int ssl_b200_loss_forward_backward(const void* sr, const void* gt, in
         if (int e = ssl_b200_ssg_rows_backward(sr, dtype, B, C, H, W, edges, counts, max_edges, ks, kw, rows_sr,
                                                grad_sr, stream)) return e;
     return 0;
+}
+
+extern "C" int ssl_b200_loss_export_distance_grad(const void* workspace, size_t workspace_bytes, int B, int C, int H,
+                                                  int W, const int32_t* edges, const int32_t* counts, int max_edges,
+                                                  int ks, int kw, int path, float* gq_rows, void* stream) {
+    SSLB_REQUIRE(workspace && edges && counts && gq_rows, "null pointer");
+    SSLB_REQUIRE(workspace_bytes >= ssl_b200_loss_workspace_bytes(B, C, H, W, ks, kw, max_edges, path),
+                 "workspace too small");
+    if (max_edges <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const char* ws = static_cast<const char*>(workspace);
+    if (use_plane_path(path, B, C, H, W, ks, kw, max_edges)) {
+        SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, {
+            const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, 2 * di.sm_count, true);
+            const PlaneLists lists = carve_lists(const_cast<char*>(ws), l.lists, nullptr);
+            plane_rows_to_reference_kernel<<<min(max_edges, di.sm_count * 16), 256, 0, st>>>(
+                reinterpret_cast<const float*>(ws + l.off_q[0]), l.cap, edges, counts, max_edges, lists.slot_map, Cfg::L,
+                gq_rows);
+            return check_launch("export_distance_grad");
+        });
+    }
+    copy_rows_kernel<<<di.sm_count * 8, 256, 0, st>>>(reinterpret_cast<const float*>(ws), counts, max_edges, ks * ks,
+                                                      gq_rows);
+    return check_launch("export_distance_grad");
 }
 
 namespace {

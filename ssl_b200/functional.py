@@ -249,13 +249,16 @@ class _SSLLoss(torch.autograd.Function):
 
     The 1/N of the 'mean' is applied with the (optionally all-reduced) global element count, so the
     kernels never wait for it; the backward pass is a single scale of the stored gradient.
+    ``grad_scale`` multiplies the gradient only (parity="global_ddp": world size, see dist.py).
     """
 
     @staticmethod
-    def forward(ctx, sr, gt, el, n, ks, kw, sigma, eps, mode, w_l1, w_kl, reducer, path=0):
+    def forward(ctx, sr, gt, el, n, ks, kw, sigma, eps, mode, w_l1, w_kl, reducer, path=0, grad_scale=1.0):
         sr_c, gt_c = sr.contiguous(), gt.contiguous()
         if gt_c.dtype != sr_c.dtype:
-            gt_c = gt_c.to(sr_c.dtype)
+            # mixed precision (e.g. bf16 SR under autocast, fp32 GT): never round the target graph's input;
+            # both images go to the kernels as fp32 (the arithmetic is fp32 either way)
+            sr_c, gt_c = sr_c.float(), gt_c.float()
         dev = sr_c.device
         need_grad = ctx.needs_input_grad[0]
         c = sr_c.shape[1]
@@ -277,7 +280,7 @@ class _SSLLoss(torch.autograd.Function):
         part_l1 = (w_l1 * l1).to(torch.float32)
         part_kl = (w_kl * kl).to(torch.float32)
         ctx.grad_sr = grad
-        ctx.inv_n = (1.0 / n_tot).to(torch.float32)
+        ctx.inv_n = (grad_scale / n_tot).to(torch.float32)
         ctx.sr_dtype = sr.dtype
         ctx.mark_non_differentiable(part_l1, part_kl)  # logging values; `total` carries the gradient
         return total, part_l1, part_kl
@@ -286,9 +289,9 @@ class _SSLLoss(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_total, _g_l1, _g_kl):
         if ctx.grad_sr is None:
-            return (None,) * 13
+            return (None,) * 14
         g = (ctx.grad_sr * (g_total.to(torch.float32) * ctx.inv_n)).to(ctx.sr_dtype)
-        return (g,) + (None,) * 12
+        return (g,) + (None,) * 13
 
 
 def ssl_step_host(sr, gt, mask, kernel_size_search: int = 25, kernel_size_window: int = 9, sigma: float = 0.004,

@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import functional as F_
-from .dist import make_reducer
+from .dist import grad_scale, make_reducer
 
 
 _PATHS = {"auto": 0, "point": 1, "plane": 2}
@@ -23,7 +23,7 @@ _PATHS = {"auto": 0, "point": 1, "plane": 2}
 def ssl(sr: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None, kernel_size_search: int = 25,
         kernel_size_window: int = 9, sigma: float = 0.004, generalization: bool = True, eps: float = 1e-10,
         loss_weight: float = 1.0, kl_weight: float = 0.0, mask_stride: int = 0, mask_threshold: float = 20.0,
-        max_edges: Optional[int] = None, parity: str = "global", group=None, return_parts: bool = False,
+        max_edges: Optional[int] = None, parity: str = "ddp", group=None, return_parts: bool = False,
         path: str = "auto"):
     """Self-similarity loss of a batch.
 
@@ -34,7 +34,11 @@ def ssl(sr: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None,
     Returns ``loss_weight * mean|S_sr - S_gt| + kl_weight * KL`` as a 0-dim fp32 tensor -- the sum of
     the reference's ``l_selfsim`` and ``l_selfsim_kl``; with ``return_parts`` also the two terms
     (detached, for the loss dict).  An all-empty mask gives 0 (the reference omits the term).
-    ``max_edges`` (rows capacity) makes the call free of host syncs and CUDA-graph capturable.
+    ``max_edges`` (rows capacity) makes the call free of host syncs and CUDA-graph capturable; if the mask
+    holds more edge pixels than that, the loss and the gradient come back NaN (never a silently truncated
+    batch).
+    ``parity`` : "ddp" (default: mean over this rank's rows, what the reference does under DDP), "global"
+    or "global_ddp" (normalise by the all-reduced global count; see ssl_b200/dist.py).
     ``path``: "auto" | "point" | "plane" -- which kernels run (include/ssl_b200.h SSL_B200_PATH_*).
     """
     F_._require_cuda(sr, "sr")
@@ -52,7 +56,7 @@ def ssl(sr: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None,
     mode = F_.rows_mode(generalization)
     total, l1, kl = F_._SSLLoss.apply(sr, gt.detach(), el, n, int(kernel_size_search), int(kernel_size_window),
                                       float(sigma), float(eps), mode, float(loss_weight), float(kl_weight),
-                                      make_reducer(parity, group), _PATHS[path])
+                                      make_reducer(parity, group), _PATHS[path], grad_scale(parity, group))
     return (total, l1, kl) if return_parts else total
 
 
@@ -63,7 +67,7 @@ class SelfSimilarityLoss(nn.Module):
     def __init__(self, kernel_size_search: int = 25, kernel_size_window: int = 9, sigma: float = 0.004,
                  generalization: bool = True, eps: float = 1e-10, loss_weight: float = 1.0, kl_weight: float = 0.0,
                  mask_stride: int = 0, mask_threshold: float = 20.0, max_edges: Optional[int] = None,
-                 parity: str = "global", path: str = "auto"):
+                 parity: str = "ddp", path: str = "auto"):
         super().__init__()
         self.path = path
         self.kernel_size_search = kernel_size_search

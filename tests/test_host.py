@@ -78,7 +78,10 @@ def _gloo_worker(rank, world, port, out):
     red = make_reducer("global")
     glob = red(local)
     ddp = make_reducer("ddp")
-    out[rank] = (glob.tolist(), ddp is None, float(mean_from_terms(glob, 4)))
+    from ssl_b200.dist import grad_scale
+    out[rank] = (glob.tolist(), ddp is None, float(mean_from_terms(glob, 4)),
+                 (grad_scale("ddp"), grad_scale("global"), grad_scale("global_ddp")),
+                 make_reducer("global_ddp")(local).tolist())
     dist.destroy_process_group()
 
 
@@ -90,7 +93,9 @@ def test_global_parity_reduction_world2_gloo():
         mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
         res = dict(out)
     for r in (0, 1):
-        terms, ddp_none, mean = res[r]
+        terms, ddp_none, mean, scales, terms_gd = res[r]
+        # "global_ddp": same exchange as "global", gradient pre-multiplied by the world size (DDP divides it out)
+        assert scales == (1.0, 1.0, 2.0) and terms_gd == terms
         assert terms == [3.0, 30.0, 8.0]       # sums and row counts add across ranks
         assert ddp_none                        # reference DDP semantics: no collective
         assert mean == pytest.approx(3.0 / 32)  # normalised by the GLOBAL element count
@@ -107,3 +112,45 @@ def test_synth_is_deterministic_and_nondegenerate():
     assert float((sr - gt).abs().mean()) > 1e-3
     assert mask[:, :, 0, 0].all() and mask[:, :, -1, -1].all()
     assert 0.05 < float(mask.mean()) < 0.2
+
+
+def test_parity_default_is_the_reference_ddp_behaviour():
+    """the module must drop into a DDP trainer with the reference's semantics (local mean)."""
+    import inspect
+    import ssl_b200
+    from ssl_b200.dist import grad_scale, make_reducer
+    assert inspect.signature(ssl_b200.ssl).parameters["parity"].default == "ddp"
+    assert ssl_b200.SelfSimilarityLoss().parity == "ddp"
+    assert make_reducer("ddp") is None and grad_scale("global_ddp") == 1.0   # no process group: single device
+    with pytest.raises(ValueError):
+        make_reducer("mean")
+
+
+def test_reference_cuda_library_builds_and_exports():
+    """oracle/_ref: the reference's similarity.cu compiled unmodified (second oracle + GPU baseline)."""
+    from oracle import build_ref
+    path = build_ref.build()
+    if path is None:
+        pytest.skip("neither /root/reference nor a prebuilt oracle/_ref is present")
+    lib = ctypes.CDLL(path)
+    for name in ("ref_compute_similarity", "ref_compute_similarity_backward"):
+        assert hasattr(lib, name)
+
+
+def test_diffusion_side_defaults_and_positional_guard():
+    """defaults of the diffusion-side constructor (loss_util.py:243-247) and its third positional."""
+    import inspect
+    from ssl_b200 import similarity_map
+    src = inspect.getsource(similarity_map.__init__)
+    assert "else 4" in src and "True if softmax is None" in src
+    with pytest.raises(TypeError, match="keyword"):
+        similarity_map(torch.zeros(1, 3, 32, 32), torch.ones(1, 1, 32, 32), torch.zeros(1, 3, 32, 32))
+
+
+def test_bench_loss_golden_is_complete():
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_loss.json")))
+    assert set(g["config2_fp32"]) == {str(i) for i in range(1, 9)}
+    assert len(g["config3_bf16"]["rows_per_image"]) == 64
+    tot = sum(g["config3_bf16"]["l1_sum_per_image"]) / (sum(g["config3_bf16"]["rows_per_image"]) * 625)
+    assert tot == pytest.approx(g["config3_bf16"]["loss"], rel=1e-12)
