@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SSL_B200_ABI_VERSION 2
+#define SSL_B200_ABI_VERSION 3
 
 /* element types of image tensors */
 #define SSL_B200_F32 0
@@ -163,6 +163,23 @@ int ssl_b200_loss_forward_backward(const void* sr, const void* gt, int dtype, in
                                    const int32_t* edges, const int32_t* counts, int max_edges, int ks, int kw,
                                    float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* grad_sr,
                                    double* terms, void* workspace, size_t workspace_bytes, int path, void* stream);
+
+/* The same step straight from the edge MASK (float [B, mask_channels, H, W]; channel 0 is read, a pixel is an
+ * edge iff its value == 1.0f exactly and (mask_stride <= 1 or y % mask_stride == x % mask_stride): the rule of
+ * ssl_b200_build_edge_list).  On the plane path no flat edge list is built at all -- the per-tile lists the
+ * kernels use are made from the mask directly; on the point path the list is built inside `workspace`.
+ *   dtype_sr, dtype_gt  element types of the two images; they may differ on the plane path (e.g. bf16 SR under
+ *                autocast against an fp32 GT: neither is rounded, all arithmetic is fp32)
+ *   max_edges    capacity: the most edge pixels the caller expects.  No host round trip happens; if the mask
+ *                holds more, terms[2] (and with it the loss and the gradient scale) is NaN
+ *   terms        double [3], OVERWRITTEN: sum|S_sr - S_gt|, sum KL, n_rows (the number of edge pixels found)
+ *   workspace    ssl_b200_loss_step_workspace_bytes(...) bytes
+ * Everything else as in ssl_b200_loss_forward_backward. */
+size_t ssl_b200_loss_step_workspace_bytes(int B, int C, int H, int W, int ks, int kw, int max_edges, int path);
+int ssl_b200_loss_step(const void* sr, int dtype_sr, const void* gt, int dtype_gt, const float* mask,
+                       int mask_channels, int mask_stride, int B, int C, int H, int W, int max_edges, int ks, int kw,
+                       float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* grad_sr, double* terms,
+                       void* workspace, size_t workspace_bytes, int path, void* stream);
 
 /* Test / inspection hook: dL/dq (the gradient with respect to the raw patch distances, before the 1/N of the
  * 'mean') that the last ssl_b200_loss_forward_backward call with a non-NULL grad_sr left in `workspace`,

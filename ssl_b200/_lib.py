@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libssl_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 ROWS_RAW, ROWS_EXP, ROWS_NORM = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 PATH_AUTO, PATH_POINT, PATH_PLANE = 0, 1, 2
 
 _c_int, _c_float, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
@@ -55,6 +55,10 @@ SIGNATURES = {
                                                 _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_float,
                                                 _c_int, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p,
                                                 _c_size_t, _c_int, _c_void_p]),
+    "ssl_b200_loss_step_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
+    "ssl_b200_loss_step": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int,
+                                    _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_float,
+                                    _c_float, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_void_p]),
     "ssl_b200_loss_export_distance_grad": (_c_int, [_c_void_p, _c_size_t, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                                     _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "ssl_b200_loss_step_host": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,

@@ -46,13 +46,13 @@ inline int check_launch(const char* what, int n_kernels = 1) {
 // the launching stream; bench.py reads the per-stage milliseconds of the very launches it timed.
 enum Stage {
     kStageEdgeList = 0, kStagePlaneLists, kStageEout, kStagePlaneFwd, kStageRowLoss, kStagePlaneBwdLists,
-    kStagePlaneBwd, kStageFinish, kStagePointFwd, kStagePointBwd, kNumStages
+    kStagePlaneBwd, kStageFinish, kStagePointFwd, kStagePointBwd, kStagePad, kNumStages
 };
 
 inline const char* stage_name(int i) {
     static const char* names[kNumStages] = {"edge_list", "plane_lists", "plane_eout", "ssg_plane_fwd", "row_loss",
                                             "plane_bwd_lists", "ssg_plane_bwd", "plane_finish", "ssg_point_fwd",
-                                            "ssg_point_bwd"};
+                                            "ssg_point_bwd", "pad_images"};
     return i >= 0 && i < kNumStages ? names[i] : "?";
 }
 

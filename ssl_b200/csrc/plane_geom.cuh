@@ -18,17 +18,21 @@ namespace sslb {
 
 // Compile-time geometry of one (k_search, k_window) configuration.
 // ROWS = image rows one worker covers (its threads), G = consecutive dx per sweep thread, NWP = workers
-// per CTA (worker w takes dy = w, w+NWP, ...).  The forward uses (64, 5, 5): it needs a halo of K rows
+// per CTA (worker w takes dy = w, w+NWP, ...).  The forward uses (64, 4, 5): it needs a halo of K rows
 // on each side, so tall workers waste less; the backward has no row halo and uses (32, 4, 13).
-template <int KS_, int KW_, int ROWS_ = 64, int G_ = 5, int NWP_ = 5, int TX_ = 64>
+// MERGE: a remainder of one dx (25 = 6*4 + 1) is folded into the last group instead of getting a
+// one-plane group of its own, so the dx-groups of k_s = 25 are {4,4,4,4,4,5}.
+template <int KS_, int KW_, int ROWS_ = 64, int G_ = 4, int NWP_ = 5, int TX_ = 64, bool MERGE_ = true>
 struct PlaneCfg {
     static constexpr int KS = KS_, KW = KW_;
     static constexpr int P = KS / 2, K = KW / 2;
     static constexpr int L = KS * KS;
-    static constexpr int G = G_;           // consecutive dx handled by one sweep thread
+    static constexpr int G = G_;           // consecutive dx handled by one sweep thread (nominal group width)
     static constexpr int NWP = NWP_;       // workers per CTA
-    static constexpr int NPL = G * NWP;    // box-summed planes resident per CTA
-    static constexpr int NDXG = (KS + G - 1) / G;
+    static constexpr bool MERGE = MERGE_ && KS >= G && (KS % G) <= 1;
+    static constexpr int NDXG = MERGE ? KS / G : (KS + G - 1) / G;
+    static constexpr int GMAX = MERGE ? G + KS % G : G;   // widest group
+    static constexpr int NPL = GMAX * NWP;  // box-summed planes resident per CTA
     static constexpr int ROWS = ROWS_;     // threads of a worker = image rows it covers (incl. halo in the forward)
     static constexpr int THREADS = NWP * ROWS;
     static constexpr int NCLS = 2 * K + 1; // clip classes per axis
@@ -44,6 +48,7 @@ struct PlaneCfg {
     static constexpr int ICOL0 = ((P + 3) / 4) * 4;
     static constexpr int ICOLS = ICOL0 + SWEEP + P + 4;
     static constexpr int IPITCH = (((ICOLS + 3) / 4) | 1) * 4;  // 4 * odd: conflict-free float4 rows
+    static constexpr int TILE_FLOATS = 3 * IROWS * IPITCH;      // one TMA box {IPITCH, IROWS, 3}
     // shared ring of box-summed planes
     static constexpr int RING = 16;
     static constexpr int SRP = RING + 1;                 // odd row pitch
@@ -52,11 +57,12 @@ struct PlaneCfg {
     static_assert(KS % 2 == 1 && KW % 2 == 1 && KW <= KS && KW <= 9, "unsupported kernel sizes");
     static_assert(ROWS == 32 || ROWS == 64, "a worker is one warp or a warp pair");
     static_assert(2 * K <= CH, "gather lags the sweep by one chunk");
+    static_assert(IROWS <= 256 && IPITCH <= 256, "image tile must be one TMA box");
 };
 
 // Backward geometry that goes with a forward configuration.
 template <typename Cfg>
-using PlaneBwdGeom = PlaneCfg<Cfg::KS, Cfg::KW, 32, 4, 13, 96>;
+using PlaneBwdGeom = PlaneCfg<Cfg::KS, Cfg::KW, 32, 4, 13, 96, false>;
 
 // in-area range of window offsets for search offset t, per axis
 __host__ __device__ constexpr int rng_lo(int t, int P, int K) { return -P - t > -K ? -P - t : -K; }
@@ -83,15 +89,21 @@ struct PlaneLists {
 struct PlaneGeom {
     int B, H, W;
     int TYF, TXF, K;
+    int xs;                // forward tiles start at image column -xs (see make_geom)
     int nty, ntx;          // forward tiles per image
     int n_units;
 };
 
-inline PlaneGeom make_geom(int B, int H, int W, int TYF, int TXF, int K) {
+// Forward tile tx owns image columns [tx*TXF - xs, (tx+1)*TXF - xs).  The shift xs = (P - K) mod 4 makes the
+// first column of every tile's shared image window -- padded X = P - K - ICOL0 - xs + tx*TXF -- a multiple
+// of 4 floats: the copy engine wants the start of a box 16-byte aligned in global memory, and the kernels
+// want the window's own columns float4-aligned in shared memory (ICOL0 is a multiple of 4).
+inline PlaneGeom make_geom(int B, int H, int W, int TYF, int TXF, int K, int P) {
     PlaneGeom g;
     g.B = B; g.H = H; g.W = W; g.TYF = TYF; g.TXF = TXF; g.K = K;
+    g.xs = (P - K) % 4;
     g.nty = (H + TYF - 1) / TYF;
-    g.ntx = (W + TXF - 1) / TXF;
+    g.ntx = (W + g.xs + TXF - 1) / TXF;
     g.n_units = B * g.nty * g.ntx * (TXF / 8);
     return g;
 }
@@ -151,12 +163,12 @@ __global__ void __launch_bounds__(256) plane_units_count_kernel(PlaneListParams 
     if (warp >= p.g.n_units) return;
     int b, ty, tx, cx;
     decode_unit(p.g, warp, b, ty, tx, cx);
-    const int y0 = ty * p.g.TYF, x0 = tx * p.g.TXF + cx * 8;
+    const int y0 = ty * p.g.TYF, x0 = tx * p.g.TXF + cx * 8 - p.g.xs;
     const int ly = lane >> 3, lx = lane & 7;
     int n = 0;
     for (int yy = 0; yy < p.g.TYF; yy += 4) {
         const int y = y0 + yy + ly, x = x0 + lx;
-        const bool e = (yy + ly) < p.g.TYF && y < p.g.H && x < p.g.W && unit_is_edge(p, b, y, x);
+        const bool e = (yy + ly) < p.g.TYF && y < p.g.H && x >= 0 && x < p.g.W && unit_is_edge(p, b, y, x);
         n += __popc(__ballot_sync(0xffffffffu, e));
     }
     if (lane == 0) {
@@ -167,13 +179,13 @@ __global__ void __launch_bounds__(256) plane_units_count_kernel(PlaneListParams 
 
 // Emit pass (after the scan), one warp per unit.  The order of a unit's edge pixels inside its slot range is
 // free (slot_map / slot_pix carry the correspondence), so it is chosen for the forward gather: there a warp reads,
-// in one shared-memory instruction, the same ring position of G planes for ~6 consecutive 4-slot groups, and
+// in one shared-memory instruction, the same ring position of G planes for 32/G consecutive 4-slot groups, and
 // the bank of a slot is h = (SRP * row + column) mod 32.  Slots are counting-sorted by h and dealt out so
-// that consecutive groups get ranks n/6 apart, i.e. banks ~32/6 apart: their G-bank runs do not overlap.
+// that consecutive groups get ranks n/(32/G) apart, i.e. banks ~G apart: their G-bank runs do not overlap
+// (kSpreadRows = 32/G).
 constexpr int kUnitMaxEdges = 512;
-constexpr int kSpreadRows = 6;
 
-__global__ void __launch_bounds__(256) plane_units_emit_kernel(PlaneListParams p, int srp) {
+__global__ void __launch_bounds__(256) plane_units_emit_kernel(PlaneListParams p, int srp, int kSpreadRows) {
     __shared__ int32_t s_rc[8][kUnitMaxEdges], s_pix[8][kUnitMaxEdges];
     __shared__ uint8_t s_h[8][kUnitMaxEdges];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,13 +193,13 @@ __global__ void __launch_bounds__(256) plane_units_emit_kernel(PlaneListParams p
     if (warp >= p.g.n_units) return;
     int b, ty, tx, cx;
     decode_unit(p.g, warp, b, ty, tx, cx);
-    const int y0 = ty * p.g.TYF, x0 = tx * p.g.TXF + cx * 8;
+    const int y0 = ty * p.g.TYF, x0 = tx * p.g.TXF + cx * 8 - p.g.xs;
     const int ly = lane >> 3, lx = lane & 7;
     // 1. collect the unit's edge pixels in row-major order
     int n = 0;
     for (int yy = 0; yy < p.g.TYF; yy += 4) {
         const int y = y0 + yy + ly, x = x0 + lx;
-        const bool e = (yy + ly) < p.g.TYF && y < p.g.H && x < p.g.W && unit_is_edge(p, b, y, x);
+        const bool e = (yy + ly) < p.g.TYF && y < p.g.H && x >= 0 && x < p.g.W && unit_is_edge(p, b, y, x);
         const unsigned ball = __ballot_sync(0xffffffffu, e);
         if (e) {
             const int t = n + __popc(ball & ((1u << lane) - 1u));
@@ -275,6 +287,14 @@ __global__ void __launch_bounds__(1024) plane_units_scan_kernel(PlaneListParams 
         p.out.counts[2] = total;
         p.out.counts[3] = p.g.n_units;
     }
+}
+
+// terms[2] = number of SSG rows of a step whose lists were built straight from the mask.  More edge pixels than
+// the caller's max_edges, or more slots than the workspace holds, would drop edge pixels: the count is poisoned
+// instead, so the loss and the gradient scale come out NaN without any host round trip.
+__global__ void plane_terms_count_kernel(const int32_t* counts, int max_edges, int cap, double* terms) {
+    const bool overflow = counts[1] > max_edges || counts[2] > cap;
+    terms[2] = overflow ? __longlong_as_double(0x7ff8000000000000ll) : (double)counts[1];
 }
 
 __global__ void __launch_bounds__(256) fill_i32_kernel(int32_t* p, long long n, int32_t v) {

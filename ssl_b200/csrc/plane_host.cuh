@@ -1,6 +1,7 @@
 // Host-side launch code of the plane path (included by ssl_b200.cu only).
 #pragma once
 
+#include "pad.cuh"
 #include "plane_geom.cuh"
 #include "row_loss_t.cuh"
 #include "ssg_plane_fwd.cuh"
@@ -60,13 +61,13 @@ inline PlaneLists carve_lists(void* ws, const PlaneListsLayout& l, int32_t** uni
 
 template <typename Cfg>
 inline PlaneGeom geom_for(int B, int H, int W) {
-    return make_geom(B, H, W, Cfg::TYF, Cfg::TXF, Cfg::K);
+    return make_geom(B, H, W, Cfg::TYF, Cfg::TXF, Cfg::K, Cfg::P);
 }
 
 // mask (or flat edge list when mask == NULL) -> unit lists
 inline int launch_plane_lists(const float* mask, int mask_channels, int stride, const int32_t* edges,
                               const int32_t* n_edges_dev, int max_edges, const PlaneGeom& g, int cap, void* ws,
-                              cudaStream_t st, int srp = 17) {
+                              cudaStream_t st, int srp = 17, int spread = 8) {
     const PlaneListsLayout lay = plane_lists_layout(g, cap);
     PlaneListParams p{};
     p.mask = mask; p.mask_channels = mask_channels; p.stride = stride;
@@ -78,49 +79,85 @@ inline int launch_plane_lists(const float* mask, int mask_channels, int stride, 
     const long long npx = (long long)g.B * g.H * g.W;
     const int fill_blocks = (int)((npx + 255) / 256 < 4096 ? (npx + 255) / 256 : 4096);
     fill_i32_kernel<<<fill_blocks, 256, 0, st>>>(p.out.slot_map, npx, -1);
-    if (!mask && max_edges > 0) plane_mark_edges_kernel<<<(max_edges + 255) / 256 < 2048 ? (max_edges + 255) / 256 : 2048, 256, 0, st>>>(p);
+    int n_launch = 4;
+    if (!mask && max_edges > 0) {
+        plane_mark_edges_kernel<<<(max_edges + 255) / 256 < 2048 ? (max_edges + 255) / 256 : 2048, 256, 0, st>>>(p);
+        ++n_launch;
+    }
     const int blocks = (g.n_units * 32 + 255) / 256;
     plane_units_count_kernel<<<blocks, 256, 0, st>>>(p);
     plane_units_scan_kernel<<<1, 1024, 0, st>>>(p);
-    plane_units_emit_kernel<<<(g.n_units + 7) / 8, 256, 0, st>>>(p, srp);
-    return check_launch("plane_lists", 5);
+    plane_units_emit_kernel<<<(g.n_units + 7) / 8, 256, 0, st>>>(p, srp, spread);
+    return check_launch("plane_lists", n_launch);
+}
+
+// ---- reflect-padded fp32 copy of the batch + its tensor maps ---------------------------------
+struct PadLayout {
+    int Hp, Wp, pitch;
+    size_t bytes_per_image_set;   // B * 3 * Hp * pitch floats (a multiple of 16 bytes; two sets are contiguous)
+};
+
+inline PadLayout pad_layout(int B, int H, int W, int P) {
+    PadLayout l;
+    l.Hp = H + 2 * P; l.Wp = W + 2 * P; l.pitch = pad_pitch(W, P);
+    l.bytes_per_image_set = (size_t)B * 3 * l.Hp * l.pitch * sizeof(float);
+    return l;
+}
+
+inline int launch_pad(const void* img0, int dtype0, const void* img1, int dtype1, int B, int H, int W, int P,
+                      float* out, cudaStream_t st) {
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const PadLayout l = pad_layout(B, H, W, P);
+    PadParams pp{};
+    pp.img[0] = img0; pp.img[1] = img1; pp.dtype[0] = dtype0; pp.dtype[1] = dtype1;
+    pp.n_img = img1 ? 2 : 1;
+    pp.B = B; pp.C = 3; pp.H = H; pp.W = W; pp.P = P; pp.Hp = l.Hp; pp.Wp = l.Wp; pp.pitch = l.pitch;
+    pp.out = out;
+    StageTimer timer(kStagePad, st);
+    pad_images_kernel<<<di.sm_count * 8, 256, 0, st>>>(pp);
+    return check_launch("pad_images");
 }
 
 template <typename Cfg>
-inline int launch_plane_forward_cfg(const void* img, const void* img2, int dtype, const PlaneGeom& g,
-                                    const PlaneLists& lists, int cap, float* qT, float* qT2, float* eout,
-                                    float* eout2, cudaStream_t st) {
+inline int launch_plane_forward_cfg(const float* pad, int n_img, const PlaneGeom& g, const PlaneLists& lists, int cap,
+                                    float* qT, float* qT2, float* eout, float* eout2, cudaStream_t st) {
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
+    const PadLayout pl = pad_layout(g.B, g.H, g.W, Cfg::P);
     PlaneFwdParams p{};
-    p.img[0] = img; p.img[1] = img2;
+    p.pad = pad; p.Hp = pl.Hp; p.pitch = pl.pitch;
     p.qT[0] = qT; p.qT[1] = qT2;
     p.eout[0] = eout; p.eout[1] = eout2;
     p.lists = lists; p.g = g; p.cap = cap;
-    const int n_img = img2 ? 2 : 1;
     const size_t smem = plane_fwd_smem_bytes<Cfg>();
     SSLB_REQUIRE(smem <= (size_t)di.max_smem_optin, "plane forward needs %zu B of shared memory", smem);
     const int tiles = g.B * g.nty * g.ntx;
-    SSLB_DISPATCH_DTYPE(dtype, T, {
-        {
-            StageTimer timer(kStageEout, st);
-            plane_eout_kernel<T, Cfg><<<dim3(di.sm_count * 8, n_img), 128, 0, st>>>(p);
-        }
-        auto k = ssg_plane_fwd_kernel<T, Cfg>;
-        SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUtensorMap tmap;
+    // both image sets are one contiguous stack of n_img * B * 3 planes
+    if (int e = make_plane_map(&tmap, pad, n_img * g.B * 3, pl.Hp, pl.Wp, pl.pitch, Cfg::IPITCH, Cfg::IROWS, 3)) return e;
+    {
+        StageTimer timer(kStageEout, st);
+        plane_eout_kernel<Cfg><<<dim3(di.sm_count * 8, n_img), 128, 0, st>>>(p);
+    }
+    auto k = ssg_plane_fwd_kernel<Cfg>;
+    SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
         StageTimer timer(kStagePlaneFwd, st);
-        k<<<dim3(Cfg::NDXG, tiles, n_img), Cfg::THREADS, smem, st>>>(p);
-    });
+        k<<<dim3(Cfg::NDXG, tiles, n_img), Cfg::THREADS, smem, st>>>(tmap, p);
+    }
     return check_launch("plane_forward", 2);
 }
 
 // ---- whole plane step ---------------------------------------------------------------------
-// Workspace: lists | qT[SR] (becomes dL/dq) | qT[GT] | eout[2] | gcls | wtab | scratch | bwd lists | gpart
+// Workspace: lists | padded SR, GT | qT[SR] (becomes dL/dq) | qT[GT] | eout[2] | gcls | wtab | scratch | bwd lists | gpart
 struct PlaneStepLayout {
     PlaneGeom g;
     int cap;
     PlaneListsLayout lists;
-    size_t off_q[2], off_eout[2], off_gcls, off_wtab, off_scratch, off_tcols, off_tent, off_gpart, off_wsum, total;
+    PadLayout pad;
+    size_t off_pad, off_q[2], off_eout[2], off_gcls, off_wtab, off_scratch, off_tcols, off_tcum, off_tent, off_gpart,
+        off_wsum, total;
     int ntyb, ntxb, HT, WT, n_btiles, loss_blocks;
 };
 
@@ -132,6 +169,7 @@ inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int
     l.g = geom_for<Cfg>(B, H, W);
     l.cap = slot_capacity(max_edges, l.g.n_units);
     l.lists = plane_lists_layout(l.g, l.cap);
+    l.pad = pad_layout(B, H, W, Cfg::P);
     l.loss_blocks = loss_blocks;
     const int Hp = H + 2 * Cfg::P, Wp = W + 2 * Cfg::P;
     l.ntyb = (Hp + BG::ROWS - 1) / BG::ROWS;
@@ -141,14 +179,17 @@ inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int
     l.n_btiles = B * l.ntyb * l.ntxb;
     const size_t nc2 = (size_t)Cfg::NCLS * Cfg::NCLS;
     size_t o = l.lists.total;
+    // the two padded image sets must be contiguous (one tensor map spans both): unrounded size, rounded end
+    l.off_pad = o; o += align256(2 * l.pad.bytes_per_image_set);
     for (int i = 0; i < 2; ++i) { l.off_q[i] = o; o += align256((size_t)Cfg::L * l.cap * sizeof(float)); }
     for (int i = 0; i < 2; ++i) { l.off_eout[i] = o; o += align256((size_t)l.cap * nc2 * sizeof(float)); }
     l.off_gcls = o; o += align256((size_t)l.cap * nc2 * sizeof(float));
     l.off_wtab = o; o += align256((size_t)l.cap * Cfg::KW * Cfg::KW * sizeof(float));
     l.off_scratch = o; o += align256((size_t)2 * loss_blocks * sizeof(double));
-    l.off_tcols = o; l.off_tent = o; l.off_gpart = o; l.off_wsum = o;
+    l.off_tcols = o; l.off_tcum = o; l.off_tent = o; l.off_gpart = o; l.off_wsum = o;
     if (want_grad) {
         o += align256((size_t)l.n_btiles * (BC::RCOLS + 1) * sizeof(int32_t));
+        l.off_tcum = o; o += align256((size_t)l.n_btiles * BC::RCOLS * BC::CUM_PITCH);
         l.off_tent = o; o += align256((size_t)l.n_btiles * BC::LIST_STRIDE * sizeof(int32_t));
         l.off_gpart = o; o += align256((size_t)BG::NDXG * B * 3 * l.HT * l.WT * sizeof(float));
         l.off_wsum = o; o += align256((size_t)B * l.HT * l.WT * sizeof(float));
@@ -158,69 +199,85 @@ inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int
 }
 
 // dL/dq (offset-major, gqT) + per-class sums (gcls) -> dL/dimage.  Shared by the fused step and by the
-// rows backward of the operator API.
+// rows backward of the operator API.  `pad` = reflect-padded fp32 image the gradient is taken for.
 template <typename Cfg>
-inline int launch_plane_backward_cfg(const void* img, int dtype, int B, int H, int W, const PlaneLists& lists,
+inline int launch_plane_backward_cfg(const float* pad, int B, int H, int W, const PlaneLists& lists,
                                      const PlaneStepLayout& l, char* ws, const float* gqT, const float* gcls,
                                      float* grad_out, cudaStream_t st) {
     using BG = PlaneBwdGeom<Cfg>;
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
     PlaneBwdParams bp{};
-    bp.img = img; bp.gqT = gqT;
+    bp.gqT = gqT;
     int32_t* tcols = reinterpret_cast<int32_t*>(ws + l.off_tcols);
+    uint8_t* tcum = reinterpret_cast<uint8_t*>(ws + l.off_tcum);
     int32_t* tent = reinterpret_cast<int32_t*>(ws + l.off_tent);
-    bp.tile_cols = tcols; bp.tile_ent = tent;
+    bp.tile_cols = tcols; bp.tile_cum = tcum; bp.tile_ent = tent;
     bp.gpart = reinterpret_cast<float*>(ws + l.off_gpart);
     bp.slot_map = lists.slot_map;
     bp.B = B; bp.H = H; bp.W = W; bp.cap = l.cap;
     bp.ntyb = l.ntyb; bp.ntxb = l.ntxb; bp.HT = l.HT; bp.WT = l.WT;
     {
         StageTimer timer(kStagePlaneBwdLists, st);
-        plane_bwd_lists_kernel<BG><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tent);
+        plane_bwd_lists_kernel<BG><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tcum, tent);
     }
     const size_t smem = plane_bwd_smem_bytes<BG>();
     SSLB_REQUIRE(smem <= (size_t)di.max_smem_optin, "plane backward needs %zu B of shared memory", smem);
+    CUtensorMap tmap;
+    if (int e = make_plane_map(&tmap, pad, B * 3, l.pad.Hp, l.pad.Wp, l.pad.pitch, BG::IPITCH, BG::IROWS, 3)) return e;
     PlaneFinishParams fp{};
-    fp.img = img; fp.gpart = bp.gpart; fp.wtab = reinterpret_cast<float*>(ws + l.off_wtab);
+    fp.pad = pad; fp.Hp = l.pad.Hp; fp.pitch = l.pad.pitch;
+    fp.gpart = bp.gpart; fp.wtab = reinterpret_cast<float*>(ws + l.off_wtab);
     fp.slot_map = lists.slot_map; fp.grad = grad_out;
     fp.wsum = reinterpret_cast<float*>(ws + l.off_wsum);
     fp.B = B; fp.H = H; fp.W = W; fp.HT = l.HT; fp.WT = l.WT; fp.n_parts = BG::NDXG; fp.cap = l.cap;
     const long long npx = (long long)B * H * W;
-    SSLB_DISPATCH_DTYPE(dtype, T, {
-        auto k = ssg_plane_bwd_kernel<T, BG>;
-        SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        {
-            StageTimer timer(kStagePlaneBwd, st);
-            k<<<dim3(l.n_btiles, BG::NDXG), BG::THREADS, smem, st>>>(bp);
-        }
+    auto k = ssg_plane_bwd_kernel<BG>;
+    SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        StageTimer timer(kStagePlaneBwd, st);
+        k<<<dim3(l.n_btiles, BG::NDXG), BG::THREADS, smem, st>>>(tmap, bp);
+    }
+    {
         StageTimer timer(kStageFinish, st);
         plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(gcls, lists.counts, l.cap,
                                                                reinterpret_cast<float*>(ws + l.off_wtab));
         plane_wsum_kernel<Cfg><<<dim3(l.WT / 16, l.HT / 16, B), 256, 0, st>>>(fp);
-        plane_finish_kernel<T, Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
-    });
+        plane_finish_kernel<Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
+    }
     return check_launch("plane_backward", 5);
 }
 
+// Lists for the step: straight from the mask when there is one, from the flat edge list otherwise.
+struct StepInputs {
+    const void* sr; const void* gt; int dtype_sr, dtype_gt;
+    const float* mask; int mask_channels, mask_stride;     // mask == NULL: use edges
+    const int32_t* edges; const int32_t* n_edges_dev;
+};
+
 template <typename Cfg>
-inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int B, int H, int W, const int32_t* edges,
-                                 const int32_t* counts, int max_edges, float sigma, float eps, int rows_mode,
-                                 float w_l1, float w_kl, float* grad_sr, double* terms, void* workspace,
+inline int launch_plane_step_cfg(const StepInputs& in, int B, int H, int W, int max_edges, float sigma, float eps,
+                                 int rows_mode, float w_l1, float w_kl, float* grad_sr, double* terms, void* workspace,
                                  size_t workspace_bytes, cudaStream_t st) {
     using BG = PlaneBwdGeom<Cfg>;
-    using BC = PlaneBwdCfg<BG>;
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
     const int loss_blocks = 2 * di.sm_count;
     const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, loss_blocks, grad_sr != nullptr);
     SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
     char* ws = static_cast<char*>(workspace);
-    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st, Cfg::SRP)) return e;
+    float* pad = reinterpret_cast<float*>(ws + l.off_pad);
+    if (int e = launch_pad(in.sr, in.dtype_sr, in.gt, in.dtype_gt, B, H, W, Cfg::P, pad, st)) return e;
+    if (int e = launch_plane_lists(in.mask, in.mask_channels, in.mask_stride, in.edges, in.n_edges_dev, max_edges, l.g,
+                                   l.cap, ws, st, Cfg::SRP, 32 / Cfg::G)) return e;
     const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
+    if (in.mask) {
+        plane_terms_count_kernel<<<1, 1, 0, st>>>(lists.counts, max_edges, l.cap, terms);
+        if (int e = check_launch("plane_terms_count")) return e;
+    }
     float* q_sr = reinterpret_cast<float*>(ws + l.off_q[0]);
     float* q_gt = reinterpret_cast<float*>(ws + l.off_q[1]);
-    if (int e = launch_plane_forward_cfg<Cfg>(sr, gt, dtype, l.g, lists, l.cap, q_sr, q_gt,
+    if (int e = launch_plane_forward_cfg<Cfg>(pad, 2, l.g, lists, l.cap, q_sr, q_gt,
                                               reinterpret_cast<float*>(ws + l.off_eout[0]),
                                               reinterpret_cast<float*>(ws + l.off_eout[1]), st)) return e;
     // rows -> loss terms and dL/dq (in place over q_sr) + per-class sums
@@ -241,7 +298,7 @@ inline int launch_plane_step_cfg(const void* sr, const void* gt, int dtype, int 
     }
     if (int e = check_launch("row_loss_t", 2)) return e;
     if (!grad_sr) return 0;
-    return launch_plane_backward_cfg<Cfg>(sr, dtype, B, H, W, lists, l, ws, q_sr, rp.gcls, grad_sr, st);
+    return launch_plane_backward_cfg<Cfg>(pad, B, H, W, lists, l, ws, q_sr, rp.gcls, grad_sr, st);
 }
 
 // Rows backward behind the reference's operator API (similarity_map / compute_similarity): dL/dq rows in the
@@ -255,7 +312,9 @@ inline int launch_plane_rows_backward_cfg(const void* img, int dtype, int B, int
     const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, 2 * di.sm_count, true);
     SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
     char* ws = static_cast<char*>(workspace);
-    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st, Cfg::SRP)) return e;
+    float* pad = reinterpret_cast<float*>(ws + l.off_pad);
+    if (int e = launch_pad(img, dtype, nullptr, dtype, B, H, W, Cfg::P, pad, st)) return e;
+    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st, Cfg::SRP, 32 / Cfg::G)) return e;
     const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
     float* gqT = reinterpret_cast<float*>(ws + l.off_q[0]);
     float* gcls = reinterpret_cast<float*>(ws + l.off_gcls);
@@ -271,7 +330,7 @@ inline int launch_plane_rows_backward_cfg(const void* img, int dtype, int B, int
         plane_class_sums_kernel<<<di.sm_count * 8, 256, 0, st>>>(gqT, lists.counts, l.cap, Cfg::KS, Cfg::P, Cfg::K, gcls);
     }
     if (int e = check_launch("plane_rows_to_slots", 3)) return e;
-    return launch_plane_backward_cfg<Cfg>(img, dtype, B, H, W, lists, l, ws, gqT, gcls, grad, st);
+    return launch_plane_backward_cfg<Cfg>(pad, B, H, W, lists, l, ws, gqT, gcls, grad, st);
 }
 
 }  // namespace sslb

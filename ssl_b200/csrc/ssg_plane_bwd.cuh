@@ -16,6 +16,8 @@
 // are ordered by per-chunk tickets (deterministic summation order, no atomics).
 #pragma once
 
+#include <cuda/atomic>
+
 #include "plane_geom.cuh"
 #include "ssg_plane_fwd.cuh"
 
@@ -27,23 +29,30 @@ struct PlaneBwdCfg {
     static constexpr int TXB = Cfg::TXF;                 // same sweep geometry as the forward
     static constexpr int NCHB = TXB / 8 + 1;
     static constexpr int ACC_PITCH = TXB + 4;            // 4 * odd
-    static constexpr int U_COL = Cfg::ROWS + 4;          // one u column: ROWS rows + the slot the last "-val" lands in
-    static constexpr int U_PLANE = 8 * U_COL;            // [8 columns][U_COL]
-    static constexpr int U_WORKER = G * U_PLANE;
-    // edge-pixel region a tile needs: rows [Yb0-P, Yb0+64+P), columns [Xb0-P-8, Xb0+TXB+P)
+    // Per-worker staging buffer of one chunk's sparse columns (G planes x 8 columns = 32 columns x ROWS rows),
+    // used in two layouts one after the other:
+    //   A[row][lane]      pitch 32: while the +val/-val events are entered, lane l owns column l and every one
+    //                     of its addresses lies in bank l -- the updates cannot conflict whatever their rows are;
+    //   B[row][column]    pitch 36 (4 * odd): the prefix-summed columns, read by the sweep (lane = row) as two
+    //                     conflict-free float4 per plane.
+    static constexpr int UB_PITCH = 36;
+    static constexpr int U_WORKER = Cfg::ROWS * UB_PITCH;
+    // edge-pixel region a tile needs: rows [Yb0-P, Yb0+ROWS+P), columns [Xb0-P-8, Xb0+TXB+P)
     static constexpr int RROWS = Cfg::ROWS + 2 * P;
     static constexpr int RCOLS = TXB + 2 * P + 8;
     static constexpr int LIST_STRIDE = RROWS * RCOLS;    // worst case entries per tile
     static constexpr int LIST_SMEM = 2560;               // entries staged in shared memory
+    static constexpr int CUM_PITCH = (RROWS + 1 + 3) & ~3;  // per column: entries above each region row (uint8)
     static_assert((ACC_PITCH / 4) % 2 == 1, "accumulator rows must be float4 conflict-free");
-    static_assert(G * 8 <= Cfg::ROWS, "one thread per (plane, u-column) when placing");
+    static_assert(G * 8 == 32 && Cfg::ROWS == 32, "one lane per (plane, u-column) when placing");
     static_assert(Cfg::NDXG <= 7, "dx-group dispatch");
+    static_assert(RROWS < 256, "row counts are stored in a byte");
 };
 
 struct PlaneBwdParams {
-    const void* img;          // SR image [B,3,H,W]
     const float* gqT;         // [L][cap]
     const int32_t* tile_cols; // [n_btiles][RCOLS+1] column starts inside the tile's entry list
+    const uint8_t* tile_cum;  // [n_btiles][RCOLS][CUM_PITCH] entries of the column above region row rr
     const int32_t* tile_ent;  // [n_btiles][LIST_STRIDE] (slot << 8) | region row
     float* gpart;             // [NDXG][B][3][HT][WT] partial padded gradients
     const int32_t* slot_map;
@@ -52,9 +61,12 @@ struct PlaneBwdParams {
 };
 
 // ---- per-tile edge lists by column ---------------------------------------------------------
-// One block per backward tile.  Entries of a column are in ascending row order.
+// One block per backward tile.  Entries of a column are in ascending row order; cum[col][rr] counts the
+// entries of the column that lie above region row rr, so the entries whose run reaches the tile for a given
+// (kind, dy) are the contiguous range [cum[rr_lo], cum[rr_hi + 1]).
 template <typename Cfg>
-__global__ void __launch_bounds__(256) plane_bwd_lists_kernel(PlaneBwdParams p, int32_t* tile_cols, int32_t* tile_ent) {
+__global__ void __launch_bounds__(256) plane_bwd_lists_kernel(PlaneBwdParams p, int32_t* tile_cols, uint8_t* tile_cum,
+                                                              int32_t* tile_ent) {
     using BC = PlaneBwdCfg<Cfg>;
     constexpr int P = Cfg::P;
     __shared__ int cnt[BC::RCOLS + 1];
@@ -83,70 +95,94 @@ __global__ void __launch_bounds__(256) plane_bwd_lists_kernel(PlaneBwdParams p, 
     __syncthreads();
     int32_t* cols = tile_cols + (long long)t * (BC::RCOLS + 1);
     for (int i = threadIdx.x; i <= BC::RCOLS; i += blockDim.x) cols[i] = cnt[i];
-    if (colok) {
+    if (col < BC::RCOLS) {
+        uint8_t* cum = tile_cum + ((long long)t * BC::RCOLS + col) * BC::CUM_PITCH;
         int32_t* ent = tile_ent + (long long)t * BC::LIST_STRIDE + cnt[col];
+        int n = 0;
         for (int rr = 0; rr < BC::RROWS; ++rr) {
+            cum[rr] = (uint8_t)n;
             const int y = y0 + rr;
-            if (y < 0 || y >= p.H) continue;
+            if (!colok || y < 0 || y >= p.H) continue;
             const int slot = p.slot_map[(b * p.H + y) * p.W + x];
-            if (slot >= 0) *ent++ = (slot << 8) | rr;
+            if (slot >= 0) { ent[n] = (slot << 8) | rr; ++n; }
         }
+        for (int rr = BC::RROWS; rr < BC::CUM_PITCH; ++rr) cum[rr] = (uint8_t)n;
     }
 }
 
-// Building one column of one sparse plane (the thread owns u[column][0..ROWS-1]) is split in two so
-// that the loads of dL/dq can be issued one chunk ahead and fly while the sweep of the current chunk
-// computes:  place_fetch (entries + loads into registers)  ...sweep...  place_apply.
+// Building one column of one sparse plane (lane (plane pj, column c8) owns it) is split in two so that the
+// loads of dL/dq can be issued one chunk ahead and fly while the sweep of the current chunk computes:
+//     place_fetch (entry range + the first NB loads into registers)  ...sweep...  place_apply.
 //
 // Every edge pixel that lands in the column covers a run of rows [r0, r1] (the v-direction of the box);
-// it is entered as +val at r0 and -val at r1+1 and the column is then prefix-summed in place, so the
-// cost per edge pixel is two shared-memory updates instead of up to 2K+1.
+// it is entered as +val at r0 and -val at r1+1 and the column is then prefix-summed, so the cost per edge
+// pixel is two shared-memory updates instead of up to 2K+1.
 template <int NB>
 struct PlaceFetch {
     int packed[2][NB];
     float val[2][NB];
-    int e0[2], e1[2];      // entries not covered by the prefetched batch: [e0 + NB, e1)
-    int lo_off[2], hi_off[2];
-    const float* gq[2];
+    int e0[2], e1[2];      // entries of the column whose run reaches the tile: [e0, e1); [e0, e0+NB) prefetched
 };
 
-template <typename Cfg, int NB>
-__device__ __forceinline__ void place_fetch(const PlaneBwdParams& p, const int32_t* cols, const int32_t* ent, int xu,
-                                            int dy, int dx, PlaceFetch<NB>& f) {
-    using BC = PlaneBwdCfg<Cfg>;
+// rows covered by an entry at region row rr: [rr + lo_off, rr + hi_off] in tile rows
+template <typename Cfg>
+__device__ __forceinline__ void place_offsets(int kind, int dy, int& lo_off, int& hi_off) {
     constexpr int P = Cfg::P, K = Cfg::K;
     const int alo = rng_lo(dy, P, K), ahi = rng_hi(dy, P, K);
+    lo_off = kind == 0 ? -P + alo : -P - dy - ahi;
+    hi_off = kind == 0 ? -P + ahi : -P - dy - alo;
+}
+
+// row of gqT an entry's value comes from: kind 0 reads offset d, kind 1 the mirrored offset -d
+template <typename Cfg>
+__device__ __forceinline__ const float* place_source(const PlaneBwdParams& p, int kind, int dy, int dx) {
+    constexpr int P = Cfg::P;
+    const int d = kind == 0 ? (dy + P) * Cfg::KS + dx + P : (-dy + P) * Cfg::KS + (-dx) + P;
+    return p.gqT + (long long)d * p.cap;
+}
+
+template <typename Cfg, int NB>
+__device__ __forceinline__ void place_fetch(const PlaneBwdParams& p, const int32_t* cols, const uint8_t* cum,
+                                            const int32_t* ent, int xu, int dy, int dx, PlaceFetch<NB>& f) {
+    using BC = PlaneBwdCfg<Cfg>;
+    constexpr int P = Cfg::P, K = Cfg::K;
     const int blo = rng_lo(dx, P, K), bhi = rng_hi(dx, P, K);
-    const long long row1 = (long long)((dy + P) * Cfg::KS + dx + P) * p.cap;
-    const long long row2 = (long long)((-dy + P) * Cfg::KS + (-dx) + P) * p.cap;
 #pragma unroll
     for (int kind = 0; kind < 2; ++kind) {
         // region column holding the edge pixels that land in u-column xu
         const int pcol = kind == 0 ? xu - blo + P : xu + dx + bhi + P;
-        const bool ok = pcol >= 0 && pcol < BC::RCOLS;
-        f.e0[kind] = ok ? cols[pcol] : 0;
-        f.e1[kind] = ok ? cols[pcol + 1] : 0;
-        // rows covered by an entry at region row rr: [rr + lo_off, rr + hi_off] in tile rows
-        f.lo_off[kind] = kind == 0 ? -P + alo : -P - dy - ahi;
-        f.hi_off[kind] = kind == 0 ? -P + ahi : -P - dy - alo;
-        f.gq[kind] = p.gqT + (kind == 0 ? row1 : row2);
+        int lo_off, hi_off;
+        place_offsets<Cfg>(kind, dy, lo_off, hi_off);
+        // region rows whose run meets tile rows [0, ROWS)
+        const int rr_lo = max(0, -hi_off), rr_hi = min(BC::RROWS - 1, Cfg::ROWS - 1 - lo_off);
+        const bool ok = pcol >= 0 && pcol < BC::RCOLS && rr_lo <= rr_hi;
+        int e0 = 0, e1 = 0;
+        if (ok) {
+            const int base = cols[pcol];
+            const uint8_t* cc = cum + pcol * BC::CUM_PITCH;
+            e0 = base + cc[rr_lo];
+            e1 = base + cc[rr_hi + 1];
+        }
+        f.e0[kind] = e0;
+        f.e1[kind] = e1;
+        const float* gq = place_source<Cfg>(p, kind, dy, dx);
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
-            f.packed[kind][m] = f.e0[kind] + m < f.e1[kind] ? ent[f.e0[kind] + m] : -1;
-            f.val[kind][m] = f.packed[kind][m] >= 0 ? __ldg(f.gq[kind] + (f.packed[kind][m] >> 8)) : 0.f;
+            f.packed[kind][m] = e0 + m < e1 ? ent[e0 + m] : -1;
+            f.val[kind][m] = f.packed[kind][m] >= 0 ? __ldg(gq + (f.packed[kind][m] >> 8)) : 0.f;
         }
     }
 }
 
-// Enter NB edge pixels of ONE kind into the column.  Entries of a kind have distinct rows, so the NB "+val"
-// addresses are distinct, and so are the NB "-val" addresses: each half is done as NB independent loads,
-// NB adds, NB stores (two dependent shared-memory round trips per batch instead of 2*NB).  The two clamped
-// cases are kept out of shared memory: runs starting above the tile add into `head` (row 0, applied once),
-// runs ending below it need no "-val" at all (nothing reads past the last row).
+// Enter NB edge pixels of ONE kind into the lane's column A[row * 32] (A already points at the lane's bank).
+// Entries of a kind have distinct rows, so the NB "+val" addresses are distinct, and so are the NB "-val"
+// addresses: each half is NB independent loads, NB adds, NB stores.  The two clamped cases stay out of shared
+// memory: runs starting above the tile add into `head` (row 0, applied by the prefix pass), runs ending below
+// it need no "-val" at all (nothing reads past the last row).
 template <typename Cfg, int NB>
-__device__ __forceinline__ int place_batch(float* ucol, const int (&packed)[NB], const float (&val)[NB], int lo_off,
-                                           int hi_off, float& head) {
-    int r0[NB], r1[NB], n = 0;
+__device__ __forceinline__ void place_batch(float* A, const int (&packed)[NB], const float (&val)[NB], int lo_off,
+                                            int hi_off, float& head) {
+    int r0[NB], r1[NB];
     bool ok[NB];
     float cur[NB];
 #pragma unroll
@@ -154,61 +190,89 @@ __device__ __forceinline__ int place_batch(float* ucol, const int (&packed)[NB],
         const int rr = packed[m] & 255;
         r0[m] = rr + lo_off;
         r1[m] = rr + hi_off;
-        ok[m] = packed[m] >= 0 && r1[m] >= 0 && r0[m] <= Cfg::ROWS - 1;
-        n += ok[m];
+        ok[m] = packed[m] >= 0;
     }
 #pragma unroll
     for (int m = 0; m < NB; ++m)
-        if (ok[m] && r0[m] > 0) cur[m] = ucol[r0[m]];
+        if (ok[m] && r0[m] > 0) cur[m] = A[r0[m] * 32];
 #pragma unroll
     for (int m = 0; m < NB; ++m)
         if (ok[m]) {
-            if (r0[m] > 0) ucol[r0[m]] = cur[m] + val[m];
+            if (r0[m] > 0) A[r0[m] * 32] = cur[m] + val[m];
             else head += val[m];
         }
 #pragma unroll
     for (int m = 0; m < NB; ++m)
-        if (ok[m] && r1[m] < Cfg::ROWS - 1) cur[m] = ucol[r1[m] + 1];
+        if (ok[m] && r1[m] < Cfg::ROWS - 1) cur[m] = A[(r1[m] + 1) * 32];
 #pragma unroll
     for (int m = 0; m < NB; ++m)
-        if (ok[m] && r1[m] < Cfg::ROWS - 1) ucol[r1[m] + 1] = cur[m] - val[m];
-    return n;
+        if (ok[m] && r1[m] < Cfg::ROWS - 1) A[(r1[m] + 1) * 32] = cur[m] - val[m];
 }
 
+// All lanes of the worker call this (it contains warp barriers); lanes without a column (active == false:
+// planes beyond the group's width) only take part in the barriers and the clearing.
+//
+// The staging buffer holds UB_PITCH * ROWS floats.  The A layout sits at its END (offset A_OFF = 4 * ROWS), the
+// B layout at its start: B row i ends at 36 (i + 1) <= A_OFF + 32 (i + 1), the start of A row i + 1, so rows can
+// be moved from A to B eight at a time (read 8 rows of the own column, warp barrier, write them as running
+// sums) without ever overwriting a row that has not been read -- 8 live registers instead of 32.
 template <typename Cfg, int NB>
-__device__ __forceinline__ void place_apply(const int32_t* ent, float* ucol, const PlaceFetch<NB>& f) {
+__device__ __forceinline__ void place_apply(const PlaneBwdParams& p, const int32_t* ent, float* ubuf, int lane,
+                                            bool active, int dy, int dx, const PlaceFetch<NB>& f) {
     using BC = PlaneBwdCfg<Cfg>;
-    float4* ucol4 = reinterpret_cast<float4*>(ucol);
+    constexpr int A_OFF = BC::U_WORKER - 32 * Cfg::ROWS;
+    static_assert(A_OFF % 4 == 0 && A_OFF >= 0, "A layout must stay float4 aligned");
+    // 1. clear the A layout (ROWS x 32 floats): ROWS/4 float4 per lane
+    float4* a4 = reinterpret_cast<float4*>(ubuf + A_OFF);
 #pragma unroll
-    for (int i = 0; i < BC::U_COL / 4; ++i) ucol4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int n_items = 0;
+    for (int i = 0; i < Cfg::ROWS / 4; ++i) a4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    // 2. events, each lane in its own bank
+    float* A = ubuf + A_OFF + lane;
     float head = 0.f;
+    if (active) {
 #pragma unroll
-    for (int kind = 0; kind < 2; ++kind) {
-        n_items += place_batch<Cfg, NB>(ucol, f.packed[kind], f.val[kind], f.lo_off[kind], f.hi_off[kind], head);
-        // columns with more than NB entries of a kind (dense masks): the rest, in batches of 4
-        for (int e = f.e0[kind] + NB; e < f.e1[kind]; e += 4) {
-            int packed[4];
-            float val[4];
+        for (int kind = 0; kind < 2; ++kind) {
+            int lo_off, hi_off;
+            place_offsets<Cfg>(kind, dy, lo_off, hi_off);
+            place_batch<Cfg, NB>(A, f.packed[kind], f.val[kind], lo_off, hi_off, head);
+            // columns with more than NB entries of a kind (dense masks): the rest, in batches of 4
+            if (f.e0[kind] + NB < f.e1[kind]) {
+                const float* gq = place_source<Cfg>(p, kind, dy, dx);
+                for (int e = f.e0[kind] + NB; e < f.e1[kind]; e += 4) {
+                    int packed[4];
+                    float val[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                packed[m] = e + m < f.e1[kind] ? ent[e + m] : -1;
-                val[m] = packed[m] >= 0 ? __ldg(f.gq[kind] + (packed[m] >> 8)) : 0.f;
+                    for (int m = 0; m < 4; ++m) {
+                        packed[m] = e + m < f.e1[kind] ? ent[e + m] : -1;
+                        val[m] = packed[m] >= 0 ? __ldg(gq + (packed[m] >> 8)) : 0.f;
+                    }
+                    place_batch<Cfg, 4>(A, packed, val, lo_off, hi_off, head);
+                }
             }
-            n_items += place_batch<Cfg, 4>(ucol, packed, val, f.lo_off[kind], f.hi_off[kind], head);
         }
     }
-    if (n_items == 0) return;  // column stays exactly zero
-    // in-place prefix sum; the four partial sums of a float4 do not wait for the running total
+    // 3. A -> B, eight rows at a time, as a running sum down the column; the partial sums of a quad do not wait
+    //    for the running total
+    float* Bc = ubuf + lane;
     float run = head;
 #pragma unroll
-    for (int i = 0; i < Cfg::ROWS / 4; ++i) {
-        float4 v = ucol4[i];
-        const float s01 = v.x + v.y, s012 = s01 + v.z, s0123 = s012 + v.w;
-        v.x += run; v.y = s01 + run; v.z = s012 + run; v.w = s0123 + run;
-        run = v.w;
-        ucol4[i] = v;
+    for (int i0 = 0; i0 < Cfg::ROWS; i0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = A[(i0 + i) * 32];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i += 4) {
+            const float s01 = v[i] + v[i + 1], s012 = s01 + v[i + 2], s0123 = s012 + v[i + 3];
+            Bc[(i0 + i) * BC::UB_PITCH] = v[i] + run;
+            Bc[(i0 + i + 1) * BC::UB_PITCH] = s01 + run;
+            Bc[(i0 + i + 2) * BC::UB_PITCH] = s012 + run;
+            run = s0123 + run;
+            Bc[(i0 + i + 3) * BC::UB_PITCH] = run;
+        }
     }
+    __syncwarp();
 }
 
 // One chunk of the h-direction tree + products for one sweep thread.
@@ -220,10 +284,10 @@ __device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* 
     float gs[GJ][8];
     BoxDispatch<0, GJ>::template run<Cfg, GC::DX0>([&](auto jc, auto lenc) {
         constexpr int j = decltype(jc)::value, len = decltype(lenc)::value;
-        const float* up = uworker + j * PlaneBwdCfg<Cfg>::U_PLANE + r;
+        const float4* up = reinterpret_cast<const float4*>(uworker + r * PlaneBwdCfg<Cfg>::UB_PITCH + j * 8);
         float cur[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = up[i * PlaneBwdCfg<Cfg>::U_COL];
+        *reinterpret_cast<float4*>(&cur[0]) = up[0];
+        *reinterpret_cast<float4*>(&cur[4]) = up[1];
         box_last<len>(cur, carry[j], gs[j]);
     });
     if (k == 0) return;  // chunk 0 only primes the tree (its outputs lie left of the tile)
@@ -247,9 +311,11 @@ __device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* 
 // Workers free-run through their own (dy, chunk) sequence.  The only shared state is the accumulator
 // tile; additions into its 8-column chunk c are serialised by a ticket per chunk, handed out in the
 // fixed order (dy-round, worker), so the summation order -- and the result -- is the same every run.
+// The ticket is a block-scope atomic: lane 0 acquires it, __syncwarp extends the ordering to the other
+// lanes, and lane 0 releases the next ticket after the warp's updates.
 template <typename Cfg, int GI>
 __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const float* tile, float* ubuf, float* accT,
-                                              const int32_t* cols, const int32_t* ent, volatile int* turn) {
+                                              const int32_t* cols, const uint8_t* cum, const int32_t* ent, int* turn) {
     using GC = GroupConsts<Cfg, GI>;
     using BC = PlaneBwdCfg<Cfg>;
     constexpr int P = Cfg::P, GJ = GC::GJ, NWP = Cfg::NWP;
@@ -258,6 +324,7 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
     float* uworker = ubuf + wp * BC::U_WORKER;
     // place-side role: (u-column c8, plane pj)
     const int c8 = r & 7, pj = r >> 3;
+    const bool placing = pj < GJ;
     BoxCarry carry[GJ];
     int idy = 0;
     for (int dy = wp - P; dy <= P; dy += NWP, ++idy) {
@@ -266,16 +333,13 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
         const int ticket = idy * NWP + wp;
         constexpr int NB = 4;  // registers are tight: 13 warps => 128 per thread
         PlaceFetch<NB> pf;
-        if (pj < GJ) place_fetch<Cfg, NB>(p, cols, ent, c8, dy, GC::DX0 + pj, pf);
+        if (placing) place_fetch<Cfg, NB>(p, cols, cum, ent, c8, dy, GC::DX0 + pj, pf);
         for (int k = 0; k < BC::NCHB; ++k) {
-            worker_sync<Cfg::ROWS>(wp);  // the previous chunk's sweep has finished reading u
-            // 1. build the chunk's 8 u-columns of every plane (one thread per column; it also clears it),
-            //    then start the loads of the next chunk's columns: they fly during the sweep below
-            if (pj < GJ) {
-                place_apply<Cfg, NB>(ent, uworker + pj * BC::U_PLANE + c8 * BC::U_COL, pf);
-                if (k + 1 < BC::NCHB) place_fetch<Cfg, NB>(p, cols, ent, 8 * (k + 1) + c8, dy, GC::DX0 + pj, pf);
-            }
-            worker_sync<Cfg::ROWS>(wp);
+            __syncwarp();  // the previous chunk's sweep has finished reading the staging buffer
+            // 1. build the chunk's 8 u-columns of every plane (one lane per column), then start the loads of
+            //    the next chunk's columns: they fly during the sweep below
+            place_apply<Cfg, NB>(p, ent, uworker, r, placing, dy, GC::DX0 + pj, pf);
+            if (placing && k + 1 < BC::NCHB) place_fetch<Cfg, NB>(p, cols, cum, ent, 8 * (k + 1) + c8, dy, GC::DX0 + pj, pf);
             // 2. h-direction + products
             float acc[3][8];
 #pragma unroll
@@ -285,12 +349,10 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
             sweep_chunk_bwd<Cfg, GI>(tile, uworker, r, dy, k, carry, acc);
             // 3. add into the accumulator tile (output chunk k-1) when it is this worker's turn
             if (k >= 1) {
-                // (flag-based hand-over: compute-sanitizer's racecheck, which only knows barriers, reports the
-                //  accumulator updates below as hazards; the fences + the volatile ticket order them)
+                cuda::atomic_ref<int, cuda::thread_scope_block> tk(turn[k - 1]);
                 if (r == 0)
-                    while (turn[k - 1] != ticket) __nanosleep(32);
-                worker_sync<Cfg::ROWS>(wp);
-                __threadfence_block();
+                    while (tk.load(cuda::memory_order_acquire) != ticket) __nanosleep(32);
+                __syncwarp();
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float4* dst = reinterpret_cast<float4*>(accT + (c * Cfg::ROWS + r) * BC::ACC_PITCH + 8 * (k - 1));
@@ -299,24 +361,26 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
                     v1.x += acc[c][4]; v1.y += acc[c][5]; v1.z += acc[c][6]; v1.w += acc[c][7];
                     dst[0] = v0; dst[1] = v1;
                 }
-                __threadfence_block();
-                worker_sync<Cfg::ROWS>(wp);
-                if (r == 0) turn[k - 1] = ticket + 1;
+                __syncwarp();
+                if (r == 0) tk.store(ticket + 1, cuda::memory_order_release);
             }
         }
     }
 }
 
-template <typename T, typename Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(PlaneBwdParams p) {
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                        PlaneBwdParams p) {
     using BC = PlaneBwdCfg<Cfg>;
-    extern __shared__ float4 plane_smem4[];
-    float* tile = reinterpret_cast<float*>(plane_smem4);
-    float* ubuf = tile + 3 * Cfg::IROWS * Cfg::IPITCH;
+    extern __shared__ __align__(1024) unsigned char plane_smem_raw[];
+    float* tile = reinterpret_cast<float*>(plane_smem_raw);
+    float* ubuf = tile + Cfg::TILE_FLOATS;
     float* accT = ubuf + Cfg::NWP * BC::U_WORKER;
     int32_t* ent_s = reinterpret_cast<int32_t*>(accT + 3 * Cfg::ROWS * BC::ACC_PITCH);
+    uint8_t* cum_s = reinterpret_cast<uint8_t*>(ent_s + BC::LIST_SMEM);
     __shared__ int32_t cols_s[BC::RCOLS + 1];
     __shared__ int turn_s[BC::NCHB];
+    __shared__ __align__(8) uint64_t tile_bar;
     if (threadIdx.x < BC::NCHB) turn_s[threadIdx.x] = 0;
     const int t = blockIdx.x;
     const int txb = t % p.ntxb, tyb = (t / p.ntxb) % p.ntyb, b = t / (p.ntxb * p.ntyb);
@@ -331,24 +395,29 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(PlaneBwd
         }
         return;
     }
-    const T* img = static_cast<const T*>(p.img) + (long long)b * 3 * p.H * p.W;
-    load_plane_tile<T, Cfg>(img, tile, p.H, p.W, Yb0 - Cfg::P, Xb0 - 8 - Cfg::ICOL0);
+    issue_tile_load<Cfg>(tile, &tmap, &tile_bar, Xb0 - 8 - Cfg::ICOL0, Yb0 - Cfg::P, b * 3);
     for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::ACC_PITCH; i += blockDim.x) accT[i] = 0.f;
     for (int i = threadIdx.x; i <= BC::RCOLS; i += blockDim.x) cols_s[i] = cols_g[i];
+    {
+        const uint32_t* cg = reinterpret_cast<const uint32_t*>(p.tile_cum + (long long)t * BC::RCOLS * BC::CUM_PITCH);
+        uint32_t* cs = reinterpret_cast<uint32_t*>(cum_s);
+        for (int i = threadIdx.x; i < BC::RCOLS * BC::CUM_PITCH / 4; i += blockDim.x) cs[i] = cg[i];
+    }
     const int32_t* ent_g = p.tile_ent + (long long)t * BC::LIST_STRIDE;
     const bool staged = n_ent <= BC::LIST_SMEM;
     if (staged)
         for (int i = threadIdx.x; i < n_ent; i += blockDim.x) ent_s[i] = ent_g[i];
     const int32_t* ent = staged ? ent_s : ent_g;
     __syncthreads();
+    mbar_wait(&tile_bar, 0);
     switch (blockIdx.y) {
-        case 0: run_group_bwd<Cfg, 0>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
-        case 1: if constexpr (Cfg::NDXG > 1) run_group_bwd<Cfg, 1>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
-        case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
-        case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
-        case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
-        case 5: if constexpr (Cfg::NDXG > 5) run_group_bwd<Cfg, 5>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
-        case 6: if constexpr (Cfg::NDXG > 6) run_group_bwd<Cfg, 6>(p, tile, ubuf, accT, cols_s, ent, turn_s); break;
+        case 0: run_group_bwd<Cfg, 0>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
+        case 1: if constexpr (Cfg::NDXG > 1) run_group_bwd<Cfg, 1>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
+        case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
+        case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
+        case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
+        case 5: if constexpr (Cfg::NDXG > 5) run_group_bwd<Cfg, 5>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
+        case 6: if constexpr (Cfg::NDXG > 6) run_group_bwd<Cfg, 6>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
         default: break;
     }
     __syncthreads();
@@ -362,8 +431,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(PlaneBwd
 template <typename Cfg>
 constexpr size_t plane_bwd_smem_bytes() {
     using BC = PlaneBwdCfg<Cfg>;
-    return (size_t)(3 * Cfg::IROWS * Cfg::IPITCH + Cfg::NWP * BC::U_WORKER + 3 * Cfg::ROWS * BC::ACC_PITCH) * sizeof(float) +
-           (size_t)BC::LIST_SMEM * sizeof(int32_t);
+    return (size_t)(Cfg::TILE_FLOATS + Cfg::NWP * BC::U_WORKER + 3 * Cfg::ROWS * BC::ACC_PITCH) * sizeof(float) +
+           (size_t)BC::LIST_SMEM * sizeof(int32_t) + (size_t)BC::RCOLS * BC::CUM_PITCH;
 }
 
 // ---- out-of-area terms and the reflect-pad adjoint -------------------------------------------
@@ -436,7 +505,8 @@ __global__ void __launch_bounds__(256) plane_class_sums_kernel(const float* gqT,
 }
 
 struct PlaneFinishParams {
-    const void* img;
+    const float* pad;         // [B][3][Hp][pitch] reflect-padded fp32 SR (image 0 of the padded buffer)
+    int Hp, pitch;
     const float* gpart;       // [NDXG][B][3][HT][WT]
     const float* wtab;        // [cap][KW*KW]
     const int32_t* slot_map;
@@ -478,9 +548,8 @@ __global__ void __launch_bounds__(256) plane_wsum_kernel(PlaneFinishParams p) {
 }
 
 // Padded-domain gradient at (Y,X) of image b, all three channels.
-template <typename T, typename Cfg>
-__device__ __forceinline__ void padded_grad_at(const PlaneFinishParams& p, const T* img, int b, int Y, int X, float (&g)[3]) {
-    constexpr int P = Cfg::P;
+template <typename Cfg>
+__device__ __forceinline__ void padded_grad_at(const PlaneFinishParams& p, int b, int Y, int X, float (&g)[3]) {
     const long long plane = (long long)p.HT * p.WT;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -490,22 +559,20 @@ __device__ __forceinline__ void padded_grad_at(const PlaneFinishParams& p, const
         g[c] = s;
     }
     const float wsum = p.wsum[(long long)b * plane + (long long)Y * p.WT + X];
-    const int sy = reflect_idx(Y - P, p.H), sx = reflect_idx(X - P, p.W);
+    const float* ip = p.pad + (long long)b * 3 * p.Hp * p.pitch + (long long)Y * p.pitch + X;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-        g[c] = fmaf(2.f * wsum, load_as_float(img + ((long long)c * p.H + sy) * p.W + sx), g[c]);
+    for (int c = 0; c < 3; ++c) g[c] = fmaf(2.f * wsum, __ldg(ip + (long long)c * p.Hp * p.pitch), g[c]);
 }
 
 // Adjoint of F.pad(reflect) (similaritywrapper.py:64) as a gather: an image pixel sums the padded
 // pixels that mirror onto it (at most 2 per axis).
-template <typename T, typename Cfg>
+template <typename Cfg>
 __global__ void __launch_bounds__(256) plane_finish_kernel(PlaneFinishParams p) {
     constexpr int P = Cfg::P;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long hw = (long long)p.H * p.W;
     if (idx >= p.B * hw) return;
     const int b = (int)(idx / hw), rem = (int)(idx - b * hw), y = rem / p.W, x = rem - y * p.W;
-    const T* img = static_cast<const T*>(p.img) + (long long)b * 3 * hw;
     int Ys[3], Xs[3], ny = 1, nx = 1;
     Ys[0] = y + P; Xs[0] = x + P;
     if (y >= 1 && y <= P) Ys[ny++] = P - y;
@@ -516,7 +583,7 @@ __global__ void __launch_bounds__(256) plane_finish_kernel(PlaneFinishParams p) 
     for (int iy = 0; iy < ny; ++iy)
         for (int ix = 0; ix < nx; ++ix) {
             float g[3];
-            padded_grad_at<T, Cfg>(p, img, b, Ys[iy], Xs[ix], g);
+            padded_grad_at<Cfg>(p, b, Ys[iy], Xs[ix], g);
             tot[0] += g[0]; tot[1] += g[1]; tot[2] += g[2];
         }
 #pragma unroll

@@ -17,11 +17,13 @@
 #include <type_traits>
 
 #include "plane_geom.cuh"
+#include "tma.cuh"
 
 namespace sslb {
 
 struct PlaneFwdParams {
-    const void* img[2];      // [B,3,H,W]; blockIdx.z selects
+    const float* pad;        // [2][B][3][Hp][pitch] reflect-padded fp32 images (pad.cuh); image 0 = SR, 1 = GT
+    int Hp, pitch;
     float* qT[2];            // [KS*KS][cap]
     const float* eout[2];    // [cap][NCLS*NCLS]
     PlaneLists lists;
@@ -33,14 +35,15 @@ struct PlaneFwdParams {
 // eout[slot][ca*NCLS+cb] = sum over window offsets (a,b) outside A(ca) x A(cb) of sum_c I(p+(a,b))^2.
 // One warp per slot.  The complement of a clip range is a prefix or a suffix of the window, so every
 // entry is a sum of at most two running sums (all terms non-negative, no subtraction).
-template <typename T, typename Cfg>
+template <typename Cfg>
 __global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
-    constexpr int K = Cfg::K, KW = Cfg::KW, NC = Cfg::NCLS, NW = KW * KW;
+    constexpr int K = Cfg::K, KW = Cfg::KW, NC = Cfg::NCLS, NW = KW * KW, P = Cfg::P;
     // sOut[a][m]: sum of the first m (m <= K) window columns of row a; sOut[a][K+1+m]: of the last m; sFull[a]: all
     __shared__ float sE[4][NW], sPre[4][KW][K + 1], sSuf[4][KW][K + 1], sFull[4][KW];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_slots = min(p.lists.counts[0], p.cap);
     const int H = p.g.H, W = p.g.W;
+    const long long plane = (long long)p.Hp * p.pitch;
     for (int slot = blockIdx.x * 4 + w; slot < n_slots; slot += gridDim.x * 4) {
         const int pix = p.lists.slot_pix[slot];
         float* out = const_cast<float*>(p.eout[blockIdx.y]) + (long long)slot * (NC * NC);
@@ -49,14 +52,13 @@ __global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
             continue;
         }
         const int hw = H * W, b = pix / hw, rem = pix - b * hw, y = rem / W, x = rem - y * W;
-        const T* img = static_cast<const T*>(p.img[blockIdx.y]) + (long long)b * 3 * hw;
+        const float* img = p.pad + ((long long)blockIdx.y * p.g.B + b) * 3 * plane + (long long)(y + P) * p.pitch + x + P;
         for (int i = lane; i < NW; i += 32) {
             const int a = i / KW - K, bb = i % KW - K;
-            const int sy = reflect_idx(y + a, H), sx = reflect_idx(x + bb, W);
             float e = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float v = load_as_float(img + (long long)c * hw + sy * W + sx);
+                const float v = __ldg(img + c * plane + a * p.pitch + bb);
                 e = fmaf(v, v, e);
             }
             sE[w][i] = e;
@@ -104,42 +106,16 @@ __global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
 }
 
 // ---- shared image tile -------------------------------------------------------------------
-// tile[c][row][col]: row 0 <-> padded Y = Ytile0 - K - P, col ICOL0 <-> padded X = Xtile0 - K;
-// reflect pad of loss_util.py:189-191 by index mapping, zero outside the padded image.
-template <typename T, typename Cfg>
-__device__ __forceinline__ void load_plane_tile(const T* img, float* tile, int H, int W, int Yrow0, int Xcol0) {
-    constexpr int P = Cfg::P, NCOLIT = (Cfg::IPITCH + 31) / 32;
-    const int Hp = H + 2 * P, Wp = W + 2 * P;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    int sx[NCOLIT];
-#pragma unroll
-    for (int m = 0; m < NCOLIT; ++m) {
-        const int X = Xcol0 + lane + 32 * m;
-        sx[m] = (X >= 0 && X < Wp && lane + 32 * m < Cfg::IPITCH) ? reflect_idx(X - P, W) : -1;
-    }
-    // RU rows per step: RU * NCOLIT independent global loads in flight per thread
-    constexpr int RU = 4;
-    for (int rr0 = warp * RU; rr0 < 3 * Cfg::IROWS; rr0 += nwarps * RU) {
-        float v[RU][NCOLIT];
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-            const int rr = rr0 + u;
-            const int c = rr / Cfg::IROWS, row = rr - c * Cfg::IROWS;
-            const int Y = Yrow0 + row;
-            const bool rowok = rr < 3 * Cfg::IROWS && Y >= 0 && Y < Hp;
-            const T* src = img + ((long long)c * H + (rowok ? reflect_idx(Y - P, H) : 0)) * W;
-#pragma unroll
-            for (int m = 0; m < NCOLIT; ++m) v[u][m] = (rowok && sx[m] >= 0) ? load_as_float(src + sx[m]) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-            const int rr = rr0 + u;
-            if (rr < 3 * Cfg::IROWS) {
-#pragma unroll
-                for (int m = 0; m < NCOLIT; ++m)
-                    if (lane + 32 * m < Cfg::IPITCH) tile[rr * Cfg::IPITCH + lane + 32 * m] = v[u][m];
-            }
-        }
+// tile[c][row][col]: row 0 <-> padded Y = Ytile0 - K - P, col ICOL0 <-> padded X = Xtile0 - K, filled by ONE
+// 3-D tensor copy from the padded images (tma.cuh); the copy engine supplies zeros outside the padded image.
+template <typename Cfg>
+__device__ __forceinline__ void issue_tile_load(float* tile, const CUtensorMap* map, uint64_t* bar, int Xcol0, int Yrow0,
+                                                int plane0) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar, (uint32_t)(Cfg::TILE_FLOATS * sizeof(float)));
+        tma_load_3d(tile, map, bar, Xcol0, Yrow0, plane0);
     }
 }
 
@@ -214,9 +190,10 @@ struct BoxDispatch {
 template <typename Cfg, int GI>
 struct GroupConsts {
     static constexpr int DX0 = -Cfg::P + GI * Cfg::G;
-    static constexpr int GJ = (Cfg::KS - GI * Cfg::G) < Cfg::G ? (Cfg::KS - GI * Cfg::G) : Cfg::G;
+    static constexpr int GJ = GI == Cfg::NDXG - 1 ? Cfg::KS - GI * Cfg::G : Cfg::G;   // the last group takes the rest
     static constexpr int OFF = ((DX0 % 4) + 4) % 4;
     static constexpr int NV4 = (OFF + 8 + GJ - 1 + 3) / 4;
+    static_assert(GJ >= 1 && GJ <= Cfg::GMAX, "group width");
 };
 
 // One chunk of one sweep thread: D, box sums, ring store.
@@ -250,8 +227,8 @@ __device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splane
     }
     // Ring column of plane j = sweep column + (K - hi(dx_j)): every plane is then read at column px + 2K, so
     // the G planes of one edge pixel sit in G consecutive banks for clipped and unclipped dx alike.
-    float* spa = splanes + (wp * Cfg::G) * Cfg::SPS + r * Cfg::SRP + (k & 1) * 8;   // ring half of this chunk
-    float* spb = splanes + (wp * Cfg::G) * Cfg::SPS + r * Cfg::SRP + ((k & 1) ^ 1) * 8;  // the other half
+    float* spa = splanes + (wp * Cfg::GMAX) * Cfg::SPS + r * Cfg::SRP + (k & 1) * 8;   // ring half of this chunk
+    float* spb = splanes + (wp * Cfg::GMAX) * Cfg::SPS + r * Cfg::SRP + ((k & 1) ^ 1) * 8;  // the other half
     BoxDispatch<0, GJ>::template run<Cfg, GC::DX0>([&](auto jc, auto lenc) {
         constexpr int j = decltype(jc)::value, len = decltype(lenc)::value;
         constexpr int shift = Cfg::K - rng_hi(GC::DX0 + j, Cfg::P, Cfg::K);
@@ -279,12 +256,12 @@ template <typename Cfg, int GI>
 __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const float* tile, float* splanes,
                                               const int32_t* ustart, const int32_t* slot_rc, int which) {
     using GC = GroupConsts<Cfg, GI>;
-    constexpr int P = Cfg::P, K = Cfg::K, G = Cfg::G, GJ = GC::GJ, NC = Cfg::NCLS;
+    constexpr int P = Cfg::P, K = Cfg::K, G = Cfg::GMAX, GJ = GC::GJ, NC = Cfg::NCLS;
     constexpr int NGRP = Cfg::ROWS / GJ;  // slot groups handled in parallel by one worker
     const int tid = threadIdx.x;
     const int wp = tid / Cfg::ROWS, r = tid % Cfg::ROWS;
-    float* qT = p.qT[which];
-    const float* eout = p.eout[which];
+    float* qT = which ? p.qT[1] : p.qT[0];
+    const float* eout = which ? p.eout[1] : p.eout[0];
     const int cap = p.cap;
     const int slot0 = ustart[0];  // slot_rc is indexed relative to the tile's first slot
     // gather-side role of this thread
@@ -373,14 +350,16 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
     }
 }
 
-template <typename T, typename Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(PlaneFwdParams p) {
-    extern __shared__ float4 plane_smem4[];
-    float* tile = reinterpret_cast<float*>(plane_smem4);
-    float* splanes = tile + 3 * Cfg::IROWS * Cfg::IPITCH;
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                        PlaneFwdParams p) {
+    extern __shared__ __align__(1024) unsigned char plane_smem_raw[];
+    float* tile = reinterpret_cast<float*>(plane_smem_raw);
+    float* splanes = tile + Cfg::TILE_FLOATS;
     int32_t* rc_s = reinterpret_cast<int32_t*>(splanes + Cfg::NPL * Cfg::SPS + 3);  // keep 16-byte alignment below
     rc_s = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(rc_s) + 15) & ~(uintptr_t)15);
     __shared__ int32_t ustart_s[Cfg::UNITS_X + 1];
+    __shared__ __align__(8) uint64_t tile_bar;
     // the dx-groups of one tile are neighbours in launch order: they share the tile's image data in L2
     const int t = blockIdx.y;
     const int tx = t % p.g.ntx, ty = (t / p.g.ntx) % p.g.nty, b = t / (p.g.ntx * p.g.nty);
@@ -389,16 +368,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(PlaneFwd
     const int slot1 = min(p.lists.unit_start[unit0 + Cfg::UNITS_X], p.cap);
     if (slot0 >= slot1) return;  // no edge pixel in this tile
     const int which = blockIdx.z;
-    const T* img = static_cast<const T*>(p.img[which]) + (long long)b * 3 * p.g.H * p.g.W;
-    // padded coordinates of the tile's first edge-pixel position: (P + ty*TYF, P + tx*TXF)
-    load_plane_tile<T, Cfg>(img, tile, p.g.H, p.g.W, Cfg::P + ty * Cfg::TYF - Cfg::K - Cfg::P,
-                            Cfg::P + tx * Cfg::TXF - Cfg::K - Cfg::ICOL0);
+    // padded coordinates of the tile's first edge-pixel position: (P + ty*TYF, P + tx*TXF - xs); the window's
+    // first column is a multiple of 4 (make_geom), as the copy engine requires
+    issue_tile_load<Cfg>(tile, &tmap, &tile_bar, Cfg::P + tx * Cfg::TXF - p.g.xs - Cfg::K - Cfg::ICOL0,
+                         Cfg::P + ty * Cfg::TYF - Cfg::K - Cfg::P, (which * p.g.B + b) * 3);
     if (threadIdx.x <= Cfg::UNITS_X) ustart_s[threadIdx.x] = p.lists.unit_start[unit0 + threadIdx.x];
     const bool staged = slot1 - slot0 <= Cfg::RC_SMEM;
     if (staged)
         for (int i = threadIdx.x; i < slot1 - slot0; i += blockDim.x) rc_s[i] = p.lists.slot_rc[slot0 + i];
     const int32_t* slot_rc = staged ? rc_s : p.lists.slot_rc + slot0;
-    __syncthreads();
+    __syncthreads();             // barrier initialised (thread 0) and lists staged
+    mbar_wait(&tile_bar, 0);     // the tile has landed
     switch (blockIdx.x) {
         case 0: run_group_fwd<Cfg, 0>(p, tile, splanes, ustart_s, slot_rc, which); break;
         case 1: if constexpr (Cfg::NDXG > 1) run_group_fwd<Cfg, 1>(p, tile, splanes, ustart_s, slot_rc, which); break;
@@ -413,7 +393,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(PlaneFwd
 
 template <typename Cfg>
 constexpr size_t plane_fwd_smem_bytes() {
-    return (size_t)(3 * Cfg::IROWS * Cfg::IPITCH + Cfg::NPL * Cfg::SPS + 8) * sizeof(float) +
+    return (size_t)(Cfg::TILE_FLOATS + Cfg::NPL * Cfg::SPS + 8) * sizeof(float) +
            (size_t)Cfg::RC_SMEM * sizeof(int32_t);
 }
 

@@ -251,12 +251,12 @@ extern "C" int ssl_b200_plane_supported(int ks, int kw, int channel) { return pl
 
 namespace {
 
-// Workspace of a plane forward: lists | qT | qT2 | eout | eout2
+// Workspace of a plane forward: lists | padded images | qT | qT2 | eout | eout2
 struct PlaneFwdLayout {
     PlaneGeom g;
     int cap;
     PlaneListsLayout lists;
-    size_t off_q[2], off_eout[2], total;
+    size_t off_pad, off_q[2], off_eout[2], total;
 };
 
 template <typename Cfg>
@@ -266,10 +266,17 @@ PlaneFwdLayout plane_fwd_layout(int B, int H, int W, int max_edges) {
     l.cap = slot_capacity(max_edges, l.g.n_units);
     l.lists = plane_lists_layout(l.g, l.cap);
     size_t o = l.lists.total;
+    l.off_pad = o; o += align256(2 * pad_layout(B, H, W, Cfg::P).bytes_per_image_set);
     for (int i = 0; i < 2; ++i) { l.off_q[i] = o; o += align256((size_t)Cfg::L * l.cap * sizeof(float)); }
     for (int i = 0; i < 2; ++i) { l.off_eout[i] = o; o += align256((size_t)l.cap * Cfg::NCLS * Cfg::NCLS * sizeof(float)); }
     l.total = o;
     return l;
+}
+
+// The backward column lists pack (slot << 8 | row) into an int32: slots must stay below 2^23.
+bool plane_slots_fit(int B, int H, int W, int max_edges) {
+    // (upper bound of the unit count over every plane geometry: TYF >= 48, TXF = 64, 8 units per tile row)
+    return (long long)max_edges + 3ll * B * (H / 48 + 1) * (W / 64 + 2) * 8 < (1ll << 23);
 }
 
 }  // namespace
@@ -293,11 +300,14 @@ extern "C" int ssl_b200_plane_rows_forward(const void* image, const void* image2
         const PlaneFwdLayout l = plane_fwd_layout<Cfg>(B, H, W, max_edges);
         SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
         char* ws = static_cast<char*>(workspace);
-        if (int e = launch_plane_lists(nullptr, 1, 0, edges, n_edges_dev, max_edges, l.g, l.cap, ws, st, Cfg::SRP)) return e;
+        float* pad = reinterpret_cast<float*>(ws + l.off_pad);
+        if (int e = launch_pad(image, dtype, image2, dtype, B, H, W, Cfg::P, pad, st)) return e;
+        if (int e = launch_plane_lists(nullptr, 1, 0, edges, n_edges_dev, max_edges, l.g, l.cap, ws, st, Cfg::SRP,
+                                       32 / Cfg::G)) return e;
         const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
         float* q0 = reinterpret_cast<float*>(ws + l.off_q[0]);
         float* q1 = image2 ? reinterpret_cast<float*>(ws + l.off_q[1]) : nullptr;
-        if (int e = launch_plane_forward_cfg<Cfg>(image, image2, dtype, l.g, lists, l.cap, q0, q1,
+        if (int e = launch_plane_forward_cfg<Cfg>(pad, image2 ? 2 : 1, l.g, lists, l.cap, q0, q1,
                                                   reinterpret_cast<float*>(ws + l.off_eout[0]),
                                                   image2 ? reinterpret_cast<float*>(ws + l.off_eout[1]) : nullptr, st))
             return e;
@@ -339,6 +349,9 @@ extern "C" int ssl_b200_plane_rows_backward(const void* image, int dtype, int B,
                                             size_t workspace_bytes, void* stream) {
     SSLB_REQUIRE(image && edges && n_edges_dev && gq && grad_image && workspace, "null pointer");
     SSLB_REQUIRE(plane_supported(ks, kw, C), "no plane kernels for k_s=%d k_w=%d C=%d", ks, kw, C);
+    if (!plane_slots_fit(B, H, W, max_edges))
+        return fail(SSL_B200_ENOTSUP, "batch too large for the plane path (%d edge pixels); use the point kernels",
+                    max_edges);
     if (int e = check_sizes(ks, kw, H, W, C)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     if (max_edges <= 0) {
@@ -402,8 +415,7 @@ size_t point_loss_workspace_bytes(int ks, int max_edges) {
 // kernels win (measured crossover, profiles/).
 bool use_plane_path(int path, int B, int C, int H, int W, int ks, int kw, int max_edges) {
     if (path == SSL_B200_PATH_POINT || !plane_supported(ks, kw, C)) return false;
-    // backward column lists pack (slot << 8 | row): slots must stay below 2^23
-    if ((long long)max_edges + 3ll * ((long long)B * H * W / 448 + 64) >= (1ll << 23)) return false;
+    if (!plane_slots_fit(B, H, W, max_edges)) return false;
     if (path == SSL_B200_PATH_PLANE) return true;
     return (double)max_edges >= 0.02 * (double)B * H * W;
 }
@@ -418,12 +430,13 @@ extern "C" size_t ssl_b200_loss_workspace_bytes(int B, int C, int H, int W, int 
     SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, { return plane_step_layout<Cfg>(B, H, W, max_edges, loss_blocks, true).total; });
 }
 
-extern "C" int ssl_b200_loss_forward_backward(const void* sr, const void* gt, int dtype, int B, int C, int H, int W,
-                                              const int32_t* edges, const int32_t* counts, int max_edges, int ks,
-                                              int kw, float sigma, float eps, int rows_mode, float w_l1, float w_kl,
-                                              float* grad_sr, double* terms, void* workspace, size_t workspace_bytes,
-                                              int path, void* stream) {
-    SSLB_REQUIRE(sr && gt && edges && counts && terms && workspace, "null pointer");
+namespace {
+
+// Shared body of the two whole-step entries.  `counts` = the edge list's counts (edges-based entry) or NULL
+// (mask-based entry on the plane path: the unit lists carry their own counts).
+int loss_step_impl(const StepInputs& in, const int32_t* counts, int B, int C, int H, int W, int max_edges, int ks,
+                   int kw, float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* grad_sr, double* terms,
+                   void* workspace, size_t workspace_bytes, int path, cudaStream_t st) {
     SSLB_REQUIRE(rows_mode == SSL_B200_ROWS_EXP || rows_mode == SSL_B200_ROWS_NORM,
                  "the loss is defined on exp / normalised rows");
     SSLB_REQUIRE(workspace_bytes >= ssl_b200_loss_workspace_bytes(B, C, H, W, ks, kw, max_edges, path),
@@ -433,33 +446,103 @@ extern "C" int ssl_b200_loss_forward_backward(const void* sr, const void* gt, in
     SSLB_REQUIRE(path != SSL_B200_PATH_PLANE || max_edges <= 0 || use_plane_path(path, B, C, H, W, ks, kw, max_edges),
                  "batch too large for the plane path (%d edge pixels); use SSL_B200_PATH_AUTO or _POINT", max_edges);
     if (int e = check_sizes(ks, kw, H, W, C)) return e;
-    cudaStream_t st = (cudaStream_t)stream;
     SSLB_CUDA(cudaMemsetAsync(terms, 0, 3 * sizeof(double), st));
     const bool plane = max_edges > 0 && use_plane_path(path, B, C, H, W, ks, kw, max_edges);
     if (grad_sr && !plane) SSLB_CUDA(cudaMemsetAsync(grad_sr, 0, sizeof(float) * (size_t)B * C * H * W, st));
-    set_terms_count_kernel<<<1, 1, 0, st>>>(counts, max_edges, terms);
-    if (int e = check_launch("set_terms_count")) return e;
+    if (counts) {
+        set_terms_count_kernel<<<1, 1, 0, st>>>(counts, max_edges, terms);
+        if (int e = check_launch("set_terms_count")) return e;
+    }
     if (max_edges <= 0) return 0;
     if (plane) {
         SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, {
-            return launch_plane_step_cfg<Cfg>(sr, gt, dtype, B, H, W, edges, counts, max_edges, sigma, eps, rows_mode,
-                                              w_l1, w_kl, grad_sr, terms, workspace, workspace_bytes, st);
+            return launch_plane_step_cfg<Cfg>(in, B, H, W, max_edges, sigma, eps, rows_mode, w_l1, w_kl, grad_sr, terms,
+                                              workspace, workspace_bytes, st);
         });
     }
+    SSLB_REQUIRE(in.edges && counts, "the point kernels need the flat edge list");
+    SSLB_REQUIRE(in.dtype_sr == in.dtype_gt, "the point kernels take both images in one element type");
     const size_t rows_bytes = align256((size_t)max_edges * ks * ks * sizeof(float));
     char* ws = static_cast<char*>(workspace);
     float* rows_sr = reinterpret_cast<float*>(ws);
     float* rows_gt = reinterpret_cast<float*>(ws + rows_bytes);
     double* scratch = reinterpret_cast<double*>(ws + 2 * rows_bytes);
-    if (int e = ssl_b200_ssg_rows_forward(sr, gt, dtype, B, C, H, W, edges, counts, max_edges, ks, kw, sigma, eps,
-                                          rows_mode, rows_sr, rows_gt, stream)) return e;
+    if (int e = ssl_b200_ssg_rows_forward(in.sr, in.gt, in.dtype_sr, B, C, H, W, in.edges, counts, max_edges, ks, kw, sigma,
+                                          eps, rows_mode, rows_sr, rows_gt, st)) return e;
     // rows_sr is overwritten in place by dL/dq when a gradient is wanted
     if (int e = ssl_b200_row_loss(rows_sr, rows_gt, counts, max_edges, ks, kw, C, sigma, rows_mode, w_l1, w_kl,
-                                  grad_sr ? rows_sr : nullptr, terms, scratch, stream)) return e;
+                                  grad_sr ? rows_sr : nullptr, terms, scratch, st)) return e;
     if (grad_sr)
-        if (int e = ssl_b200_ssg_rows_backward(sr, dtype, B, C, H, W, edges, counts, max_edges, ks, kw, rows_sr,
-                                               grad_sr, stream)) return e;
+        if (int e = ssl_b200_ssg_rows_backward(in.sr, in.dtype_sr, B, C, H, W, in.edges, counts, max_edges, ks, kw, rows_sr,
+                                               grad_sr, st)) return e;
     return 0;
+}
+
+struct StepExtras {   // edge list carved behind the loss workspace (mask-based entry, point path)
+    size_t off_edges, off_counts, off_elws, el_ws_bytes, total;
+};
+
+StepExtras step_extras(size_t loss_ws, int B, int H, int W, int max_edges) {
+    StepExtras x;
+    size_t o = align256(loss_ws);
+    x.off_edges = o; o += align256((size_t)(max_edges > 0 ? max_edges : 1) * sizeof(int32_t));
+    x.off_counts = o; o += align256((size_t)(2 + B) * sizeof(int32_t));
+    x.el_ws_bytes = ssl_b200_edge_list_workspace_bytes((int64_t)B * H * W);
+    x.off_elws = o; o += align256(x.el_ws_bytes);
+    x.total = o;
+    return x;
+}
+
+}  // namespace
+
+extern "C" int ssl_b200_loss_forward_backward(const void* sr, const void* gt, int dtype, int B, int C, int H, int W,
+                                              const int32_t* edges, const int32_t* counts, int max_edges, int ks,
+                                              int kw, float sigma, float eps, int rows_mode, float w_l1, float w_kl,
+                                              float* grad_sr, double* terms, void* workspace, size_t workspace_bytes,
+                                              int path, void* stream) {
+    SSLB_REQUIRE(sr && gt && edges && counts && terms && workspace, "null pointer");
+    StepInputs in{};
+    in.sr = sr; in.gt = gt; in.dtype_sr = dtype; in.dtype_gt = dtype;
+    in.mask = nullptr; in.mask_channels = 1; in.mask_stride = 0;
+    in.edges = edges; in.n_edges_dev = counts;
+    return loss_step_impl(in, counts, B, C, H, W, max_edges, ks, kw, sigma, eps, rows_mode, w_l1, w_kl, grad_sr, terms,
+                          workspace, workspace_bytes, path, (cudaStream_t)stream);
+}
+
+extern "C" size_t ssl_b200_loss_step_workspace_bytes(int B, int C, int H, int W, int ks, int kw, int max_edges,
+                                                     int path) {
+    const size_t base = ssl_b200_loss_workspace_bytes(B, C, H, W, ks, kw, max_edges, path);
+    if (base == 0 || use_plane_path(path, B, C, H, W, ks, kw, max_edges)) return base;
+    return step_extras(base, B, H, W, max_edges).total;
+}
+
+extern "C" int ssl_b200_loss_step(const void* sr, int dtype_sr, const void* gt, int dtype_gt, const float* mask,
+                                  int mask_channels, int mask_stride, int B, int C, int H, int W, int max_edges, int ks,
+                                  int kw, float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* grad_sr,
+                                  double* terms, void* workspace, size_t workspace_bytes, int path, void* stream) {
+    SSLB_REQUIRE(sr && gt && mask && terms && workspace, "null pointer");
+    SSLB_REQUIRE(B >= 1 && mask_channels >= 1 && max_edges >= 0, "bad shape");
+    SSLB_REQUIRE(workspace_bytes >= ssl_b200_loss_step_workspace_bytes(B, C, H, W, ks, kw, max_edges, path),
+                 "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    StepInputs in{};
+    in.sr = sr; in.gt = gt; in.dtype_sr = dtype_sr; in.dtype_gt = dtype_gt;
+    in.mask = mask; in.mask_channels = mask_channels; in.mask_stride = mask_stride;
+    if (max_edges > 0 && use_plane_path(path, B, C, H, W, ks, kw, max_edges))
+        return loss_step_impl(in, nullptr, B, C, H, W, max_edges, ks, kw, sigma, eps, rows_mode, w_l1, w_kl, grad_sr, terms,
+                              workspace, workspace_bytes, path, st);
+    // point kernels (sparse masks, other kernel sizes): they walk the flat edge list
+    const size_t base = ssl_b200_loss_workspace_bytes(B, C, H, W, ks, kw, max_edges, path);
+    const StepExtras x = step_extras(base, B, H, W, max_edges);
+    char* ws = static_cast<char*>(workspace);
+    int32_t* edges = reinterpret_cast<int32_t*>(ws + x.off_edges);
+    int32_t* counts = reinterpret_cast<int32_t*>(ws + x.off_counts);
+    if (int e = ssl_b200_build_edge_list(mask, B, mask_channels, H, W, mask_stride, edges, max_edges, counts,
+                                         ws + x.off_elws, x.el_ws_bytes, stream)) return e;
+    in.mask = nullptr;
+    in.edges = edges; in.n_edges_dev = counts;
+    return loss_step_impl(in, counts, B, C, H, W, max_edges, ks, kw, sigma, eps, rows_mode, w_l1, w_kl, grad_sr, terms,
+                          workspace, base, path, st);
 }
 
 extern "C" int ssl_b200_loss_export_distance_grad(const void* workspace, size_t workspace_bytes, int B, int C, int H,

@@ -150,6 +150,10 @@ def _use_plane(path: str, b: int, c: int, h: int, w: int, ks: int, kw: int, n: i
         if path == "plane":
             raise ValueError(f"no plane kernels for k_s={ks} k_w={kw} C={c}")
         return False
+    if n + 3 * b * (h // 48 + 1) * (w // 64 + 2) * 8 >= (1 << 23):   # slot packing of the backward lists (ssl_b200.cu: plane_slots_fit)
+        if path == "plane":
+            raise ValueError(f"batch too large for the plane kernels ({n} edge pixels); use path='auto' or 'point'")
+        return False
     return path == "plane" or n >= 0.02 * b * h * w
 
 
@@ -253,24 +257,28 @@ class _SSLLoss(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, sr, gt, el, n, ks, kw, sigma, eps, mode, w_l1, w_kl, reducer, path=0, grad_scale=1.0):
+    def forward(ctx, sr, gt, mask, mask_stride, n, ks, kw, sigma, eps, mode, w_l1, w_kl, reducer, path=0,
+                grad_scale=1.0):
         sr_c, gt_c = sr.contiguous(), gt.contiguous()
-        if gt_c.dtype != sr_c.dtype:
-            # mixed precision (e.g. bf16 SR under autocast, fp32 GT): never round the target graph's input;
-            # both images go to the kernels as fp32 (the arithmetic is fp32 either way)
-            sr_c, gt_c = sr_c.float(), gt_c.float()
         dev = sr_c.device
         need_grad = ctx.needs_input_grad[0]
-        c = sr_c.shape[1]
+        b, c, h, w = sr_c.shape
+        lib = _lib.load()
+        if gt_c.dtype != sr_c.dtype and not _use_plane({0: "auto", 1: "point", 2: "plane"}[int(path)], b, c, h, w, ks,
+                                                        kw, n):
+            # mixed precision (e.g. bf16 SR under autocast, fp32 GT) on the point kernels, which take one element
+            # type: never round the target graph's input -- both images go in as fp32 (the plane path reads each
+            # image in its own type; the arithmetic is fp32 either way)
+            sr_c, gt_c = sr_c.float(), gt_c.float()
         terms = torch.empty(3, dtype=torch.float64, device=dev)   # sum|d|, sum KL, n_rows
         grad = torch.empty(sr_c.shape, dtype=torch.float32, device=dev) if need_grad else None
-        b, _, h, w = sr_c.shape
-        ws_bytes = int(_lib.load().ssl_b200_loss_workspace_bytes(b, c, h, w, ks, kw, n, int(path)))
+        ws_bytes = int(lib.ssl_b200_loss_step_workspace_bytes(b, c, h, w, ks, kw, n, int(path)))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.call("ssl_b200_loss_forward_backward", _ptr(sr_c), _ptr(gt_c), _lib.dtype_code(sr_c.dtype), b, c, h, w,
-                      _ptr(el.edges), _ptr(el.counts), n, ks, kw, float(sigma), float(eps), mode, float(w_l1),
-                      float(w_kl), _ptr(grad), _ptr(terms), _ptr(ws), ws_bytes, int(path), _stream())
+            _lib.call("ssl_b200_loss_step", _ptr(sr_c), _lib.dtype_code(sr_c.dtype), _ptr(gt_c),
+                      _lib.dtype_code(gt_c.dtype), _ptr(mask), mask.shape[1], int(mask_stride), b, c, h, w, n, ks, kw,
+                      float(sigma), float(eps), mode, float(w_l1), float(w_kl), _ptr(grad), _ptr(terms), _ptr(ws),
+                      ws_bytes, int(path), _stream())
         if reducer is not None:
             terms = reducer(terms)
         n_tot = (terms[2] * (ks * ks)).clamp_min(1.0)
@@ -289,9 +297,9 @@ class _SSLLoss(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_total, _g_l1, _g_kl):
         if ctx.grad_sr is None:
-            return (None,) * 14
+            return (None,) * 15
         g = (ctx.grad_sr * (g_total.to(torch.float32) * ctx.inv_n)).to(ctx.sr_dtype)
-        return (g,) + (None,) * 13
+        return (g,) + (None,) * 14
 
 
 def ssl_step_host(sr, gt, mask, kernel_size_search: int = 25, kernel_size_window: int = 9, sigma: float = 0.004,

@@ -51,12 +51,18 @@ def ssl(sr: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None,
         mask = F_.laplacian_mask(gt.detach(), mask_threshold)
     elif mask.shape[0] != b or mask.shape[-2:] != (h, w):
         raise ValueError(f"mask {tuple(mask.shape)} does not match images {tuple(sr.shape)}")
-    el = F_.build_edge_list(mask, mask_stride, capacity=max_edges)
-    n = el.count() if max_edges is None else int(max_edges)
+    if mask.dtype != torch.float32 or not mask.is_contiguous():
+        mask = mask.contiguous().float()
+    if max_edges is None:
+        # one 4-byte device->host read to size the rows workspace; give max_edges to stay asynchronous
+        n = F_.build_edge_list(mask, mask_stride).count()
+    else:
+        n = int(max_edges)
     mode = F_.rows_mode(generalization)
-    total, l1, kl = F_._SSLLoss.apply(sr, gt.detach(), el, n, int(kernel_size_search), int(kernel_size_window),
-                                      float(sigma), float(eps), mode, float(loss_weight), float(kl_weight),
-                                      make_reducer(parity, group), _PATHS[path], grad_scale(parity, group))
+    total, l1, kl = F_._SSLLoss.apply(sr, gt.detach(), mask, int(mask_stride), n, int(kernel_size_search),
+                                      int(kernel_size_window), float(sigma), float(eps), mode, float(loss_weight),
+                                      float(kl_weight), make_reducer(parity, group), _PATHS[path],
+                                      grad_scale(parity, group))
     return (total, l1, kl) if return_parts else total
 
 
