@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libssl_b200.so")
+# SSL_B200_LIB names another build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("SSL_B200_LIB") or os.path.join(_HERE, "csrc", "libssl_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 ROWS_RAW, ROWS_EXP, ROWS_NORM = 0, 1, 2

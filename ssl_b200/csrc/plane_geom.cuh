@@ -19,7 +19,8 @@ namespace sslb {
 // Compile-time geometry of one (k_search, k_window) configuration.
 // ROWS = image rows one worker covers (its threads), G = consecutive dx per sweep thread, NWP = workers
 // per CTA (worker w takes dy = w, w+NWP, ...).  The forward uses (64, 4, 5): it needs a halo of K rows
-// on each side, so tall workers waste less; the backward has no row halo and uses (32, 4, 13).
+// on each side, so tall workers waste less; the backward has no row halo and uses (32, 4, 12): 12 warps are
+// three per scheduler, which leaves each thread 168 registers (a thirteenth warp would cap all of them at 128).
 // MERGE: a remainder of one dx (25 = 6*4 + 1) is folded into the last group instead of getting a
 // one-plane group of its own, so the dx-groups of k_s = 25 are {4,4,4,4,4,5}.
 template <int KS_, int KW_, int ROWS_ = 64, int G_ = 4, int NWP_ = 5, int TX_ = 64, bool MERGE_ = true>
@@ -62,7 +63,7 @@ struct PlaneCfg {
 
 // Backward geometry that goes with a forward configuration.
 template <typename Cfg>
-using PlaneBwdGeom = PlaneCfg<Cfg::KS, Cfg::KW, 32, 4, 13, 96, false>;
+using PlaneBwdGeom = PlaneCfg<Cfg::KS, Cfg::KW, 32, 4, 12, 96, false>;
 
 // in-area range of window offsets for search offset t, per axis
 __host__ __device__ constexpr int rng_lo(int t, int P, int K) { return -P - t > -K ? -P - t : -K; }

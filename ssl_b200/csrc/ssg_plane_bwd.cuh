@@ -23,6 +23,12 @@
 
 namespace sslb {
 
+#ifdef SSLB_EXPERIMENT_NOGQ   // timing experiment only: how much of the kernel is the dL/dq gather?
+#define SSLB_GQ(gq, packed) (1e-9f * (float)((packed) & 1023))
+#else
+#define SSLB_GQ(gq, packed) __ldg((gq) + ((packed) >> 8))
+#endif
+
 template <typename Cfg>
 struct PlaneBwdCfg {
     static constexpr int P = Cfg::P, K = Cfg::K, G = Cfg::G;
@@ -43,6 +49,11 @@ struct PlaneBwdCfg {
     static constexpr int LIST_STRIDE = RROWS * RCOLS;    // worst case entries per tile
     static constexpr int LIST_SMEM = 2560;               // entries staged in shared memory
     static constexpr int CUM_PITCH = (RROWS + 1 + 3) & ~3;  // per column: entries above each region row (uint8)
+    // work distribution over the NWP workers (run_group_bwd)
+    static constexpr int FULL_ROUNDS = Cfg::KS / Cfg::NWP;
+    static constexpr bool SPLIT_LAST = Cfg::KS % Cfg::NWP == 1 && NCHB - 1 <= Cfg::NWP;
+    static constexpr int N_ITEMS = SPLIT_LAST ? FULL_ROUNDS + 1 : (Cfg::KS + Cfg::NWP - 1) / Cfg::NWP;
+    static constexpr int NB = 8;                         // dL/dq values per kind prefetched into registers
     static_assert((ACC_PITCH / 4) % 2 == 1, "accumulator rows must be float4 conflict-free");
     static_assert(G * 8 == 32 && Cfg::ROWS == 32, "one lane per (plane, u-column) when placing");
     static_assert(Cfg::NDXG <= 7, "dx-group dispatch");
@@ -169,7 +180,7 @@ __device__ __forceinline__ void place_fetch(const PlaneBwdParams& p, const int32
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
             f.packed[kind][m] = e0 + m < e1 ? ent[e0 + m] : -1;
-            f.val[kind][m] = f.packed[kind][m] >= 0 ? __ldg(gq + (f.packed[kind][m] >> 8)) : 0.f;
+            f.val[kind][m] = f.packed[kind][m] >= 0 ? SSLB_GQ(gq, f.packed[kind][m]) : 0.f;
         }
     }
 }
@@ -230,7 +241,11 @@ __device__ __forceinline__ void place_apply(const PlaneBwdParams& p, const int32
     // 2. events, each lane in its own bank
     float* A = ubuf + A_OFF + lane;
     float head = 0.f;
+#ifdef SSLB_EXPERIMENT_NOPLACE
+    if (active && f.val[0][0] == 123.456f) {
+#else
     if (active) {
+#endif
 #pragma unroll
         for (int kind = 0; kind < 2; ++kind) {
             int lo_off, hi_off;
@@ -245,7 +260,7 @@ __device__ __forceinline__ void place_apply(const PlaneBwdParams& p, const int32
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
                         packed[m] = e + m < f.e1[kind] ? ent[e + m] : -1;
-                        val[m] = packed[m] >= 0 ? __ldg(gq + (packed[m] >> 8)) : 0.f;
+                        val[m] = packed[m] >= 0 ? SSLB_GQ(gq, packed[m]) : 0.f;
                     }
                     place_batch<Cfg, 4>(A, packed, val, lo_off, hi_off, head);
                 }
@@ -277,7 +292,7 @@ __device__ __forceinline__ void place_apply(const PlaneBwdParams& p, const int32
 
 // One chunk of the h-direction tree + products for one sweep thread.
 template <typename Cfg, int GI>
-__device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* uworker, int r, int dy, int k,
+__device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* uworker, int r, int dy, int k, bool prime,
                                                 BoxCarry (&carry)[GroupConsts<Cfg, GI>::GJ], float (&acc)[3][8]) {
     using GC = GroupConsts<Cfg, GI>;
     constexpr int P = Cfg::P, GJ = GC::GJ, OFF = GC::OFF, NV4 = GC::NV4;
@@ -290,7 +305,7 @@ __device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* 
         *reinterpret_cast<float4*>(&cur[4]) = up[1];
         box_last<len>(cur, carry[j], gs[j]);
     });
-    if (k == 0) return;  // chunk 0 only primes the tree (its outputs lie left of the tile)
+    if (prime) return;  // the first chunk of an item only primes the tree (its outputs belong to the chunk before)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float* rowb = tile + (c * Cfg::IROWS + r + P) * Cfg::IPITCH + Cfg::ICOL0 + 8 * k;
@@ -326,33 +341,53 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
     const int c8 = r & 7, pj = r >> 3;
     const bool placing = pj < GJ;
     BoxCarry carry[GJ];
-    int idy = 0;
-    for (int dy = wp - P; dy <= P; dy += NWP, ++idy) {
+    // Work items of this worker: whole rows of offsets dy = wp - P, wp - P + NWP, ... (chunks 0 .. NCHB-1, chunk 0
+    // only primes the h-tree), and -- when exactly one dy is left over (k_s = 25 on 12 workers) -- one output chunk
+    // of that last dy: the h-tree reaches back 2K <= 8 columns, so output chunk c needs only chunks c (priming)
+    // and c + 1.  Tickets number the additions into an output chunk in the fixed order (item, worker).
+    for (int item = 0; item < BC::N_ITEMS; ++item) {
+        int dy, k_begin, k_end;
+        if (item < BC::FULL_ROUNDS || !BC::SPLIT_LAST) {
+            dy = wp - P + item * NWP;
+            k_begin = 0;
+            k_end = BC::NCHB;
+            if (dy > P) break;
+        } else {
+            dy = P;
+            k_begin = wp;
+            k_end = wp + 2;
+            if (wp >= BC::NCHB - 1) break;
+        }
+        const int ticket = item * NWP + (item < BC::FULL_ROUNDS || !BC::SPLIT_LAST ? wp : 0);
 #pragma unroll
         for (int j = 0; j < GJ; ++j) box_carry_reset(carry[j]);
-        const int ticket = idy * NWP + wp;
-        constexpr int NB = 4;  // registers are tight: 13 warps => 128 per thread
+        constexpr int NB = BC::NB;
         PlaceFetch<NB> pf;
-        if (placing) place_fetch<Cfg, NB>(p, cols, cum, ent, c8, dy, GC::DX0 + pj, pf);
-        for (int k = 0; k < BC::NCHB; ++k) {
+        if (placing) place_fetch<Cfg, NB>(p, cols, cum, ent, 8 * k_begin + c8, dy, GC::DX0 + pj, pf);
+        for (int k = k_begin; k < k_end; ++k) {
             __syncwarp();  // the previous chunk's sweep has finished reading the staging buffer
             // 1. build the chunk's 8 u-columns of every plane (one lane per column), then start the loads of
             //    the next chunk's columns: they fly during the sweep below
             place_apply<Cfg, NB>(p, ent, uworker, r, placing, dy, GC::DX0 + pj, pf);
-            if (placing && k + 1 < BC::NCHB) place_fetch<Cfg, NB>(p, cols, cum, ent, 8 * (k + 1) + c8, dy, GC::DX0 + pj, pf);
+            if (placing && k + 1 < k_end) place_fetch<Cfg, NB>(p, cols, cum, ent, 8 * (k + 1) + c8, dy, GC::DX0 + pj, pf);
             // 2. h-direction + products
             float acc[3][8];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
-            sweep_chunk_bwd<Cfg, GI>(tile, uworker, r, dy, k, carry, acc);
+            sweep_chunk_bwd<Cfg, GI>(tile, uworker, r, dy, k, k == k_begin, carry, acc);
             // 3. add into the accumulator tile (output chunk k-1) when it is this worker's turn
-            if (k >= 1) {
+            if (k > k_begin) {
                 cuda::atomic_ref<int, cuda::thread_scope_block> tk(turn[k - 1]);
+#ifndef SSLB_EXPERIMENT_NOTICKET
                 if (r == 0)
                     while (tk.load(cuda::memory_order_acquire) != ticket) __nanosleep(32);
+#endif
                 __syncwarp();
+#ifdef SSLB_EXPERIMENT_NOACC
+                if (acc[0][0] == 123.456f)
+#endif
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float4* dst = reinterpret_cast<float4*>(accT + (c * Cfg::ROWS + r) * BC::ACC_PITCH + 8 * (k - 1));
