@@ -75,10 +75,21 @@ __host__ __device__ constexpr int clip_class(int t, int P, int K) {
 __host__ __device__ constexpr int class_lo(int cls, int K) { return cls < K ? -cls : -K; }
 __host__ __device__ constexpr int class_hi(int cls, int K) { return cls > K ? 2 * K - cls : K; }
 
+// Layout of the rows buffers (q of SR, q of GT, dL/dq): panels of kPanel = 16 consecutive slots, each panel holding
+// all L offsets of its slots contiguously:
+//     element (offset d, slot s)  at  ((s / 16) * L + d) * 16 + s % 16
+// A panel is the unit of work of the row-loss kernel (L * 64 bytes, one contiguous stream), the 4 results a forward
+// gather thread produces for one offset are still one aligned float4, and the G planes of a dx-group (consecutive
+// offsets) of one slot group are G consecutive 64-byte segments.  Capacities are multiples of 16.
+constexpr int kPanel = 16;
+__host__ __device__ __forceinline__ long long qt_index(int d, int slot, int L) {
+    return ((long long)(slot >> 4) * L + d) * kPanel + (slot & (kPanel - 1));
+}
+
 // Edge pixels regrouped for the plane kernels.  A *unit* is an 8-column strip of a forward tile;
 // its edge pixels occupy consecutive *slots* (row-major inside the unit, count padded to a multiple
 // of 4 with empty slots) so that the 4 results a lane produces for one search offset are one
-// aligned float4 of the offset-major rows buffer  qT[offset][slot].
+// aligned float4 of the rows buffer (panel layout, qt_index).
 struct PlaneLists {
     int32_t* unit_start;   // [n_units + 1] first slot of each unit (exclusive scan of padded counts)
     int32_t* slot_pix;     // [capacity] flat pixel index b*H*W + y*W + x, or -1 (padding)

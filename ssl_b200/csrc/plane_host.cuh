@@ -25,7 +25,7 @@ inline bool plane_supported(int ks, int kw, int C) {
 inline int slot_capacity(int max_edges, int n_units) {
     // every unit pads its edge count to a multiple of 4
     long long c = (long long)max_edges + 3ll * n_units;
-    c = (c + 3) & ~3ll;
+    c = (c + kPanel - 1) & ~(long long)(kPanel - 1);   // whole panels of the rows buffers
     return (int)c;
 }
 
@@ -37,7 +37,7 @@ struct PlaneListsLayout {
 inline PlaneListsLayout plane_lists_layout(const PlaneGeom& g, int cap) {
     PlaneListsLayout l;
     size_t o = 0;
-    l.off_counts = o; o += align256(4 * sizeof(int32_t));
+    l.off_counts = o; o += align256(8 * sizeof(int32_t));
     l.off_unit_start = o; o += align256((size_t)(g.n_units + 1) * sizeof(int32_t));
     l.off_unit_count = o; o += align256((size_t)g.n_units * sizeof(int32_t));
     l.off_slot_pix = o; o += align256((size_t)cap * sizeof(int32_t));
@@ -75,7 +75,7 @@ inline int launch_plane_lists(const float* mask, int mask_channels, int stride, 
     p.g = g; p.capacity = cap;
     p.out = carve_lists(ws, lay, &p.unit_count);
     StageTimer timer(kStagePlaneLists, st);
-    SSLB_CUDA(cudaMemsetAsync(p.out.counts, 0, 4 * sizeof(int32_t), st));
+    SSLB_CUDA(cudaMemsetAsync(p.out.counts, 0, 8 * sizeof(int32_t), st));   // [4] = the row loss's block counter
     const long long npx = (long long)g.B * g.H * g.W;
     const int fill_blocks = (int)((npx + 255) / 256 < 4096 ? (npx + 255) / 256 : 4096);
     fill_i32_kernel<<<fill_blocks, 256, 0, st>>>(p.out.slot_map, npx, -1);
@@ -138,7 +138,7 @@ inline int launch_plane_forward_cfg(const float* pad, int n_img, const PlaneGeom
     if (int e = make_plane_map(&tmap, pad, n_img * g.B * 3, pl.Hp, pl.Wp, pl.pitch, Cfg::IPITCH, Cfg::IROWS, 3)) return e;
     {
         StageTimer timer(kStageEout, st);
-        plane_eout_kernel<Cfg><<<dim3(di.sm_count * 8, n_img), 128, 0, st>>>(p);
+        plane_eout_kernel<Cfg><<<dim3(g.n_units, n_img), 128, 0, st>>>(p);
     }
     auto k = ssg_plane_fwd_kernel<Cfg>;
     SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -157,7 +157,7 @@ struct PlaneStepLayout {
     PlaneListsLayout lists;
     PadLayout pad;
     size_t off_pad, off_q[2], off_eout[2], off_gcls, off_wtab, off_scratch, off_tcols, off_tcum, off_tent, off_gpart,
-        off_wsum, total;
+        total;
     int ntyb, ntxb, HT, WT, n_btiles, loss_blocks;
 };
 
@@ -186,19 +186,18 @@ inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int
     l.off_gcls = o; o += align256((size_t)l.cap * nc2 * sizeof(float));
     l.off_wtab = o; o += align256((size_t)l.cap * Cfg::KW * Cfg::KW * sizeof(float));
     l.off_scratch = o; o += align256((size_t)2 * loss_blocks * sizeof(double));
-    l.off_tcols = o; l.off_tcum = o; l.off_tent = o; l.off_gpart = o; l.off_wsum = o;
+    l.off_tcols = o; l.off_tcum = o; l.off_tent = o; l.off_gpart = o;
     if (want_grad) {
         o += align256((size_t)l.n_btiles * (BC::RCOLS + 1) * sizeof(int32_t));
         l.off_tcum = o; o += align256((size_t)l.n_btiles * BC::RCOLS * BC::CUM_PITCH);
         l.off_tent = o; o += align256((size_t)l.n_btiles * BC::LIST_STRIDE * sizeof(int32_t));
         l.off_gpart = o; o += align256((size_t)BG::NDXG * B * 3 * l.HT * l.WT * sizeof(float));
-        l.off_wsum = o; o += align256((size_t)B * l.HT * l.WT * sizeof(float));
     }
     l.total = o;
     return l;
 }
 
-// dL/dq (offset-major, gqT) + per-class sums (gcls) -> dL/dimage.  Shared by the fused step and by the
+// dL/dq (offset-major, gqT) + per-class sums (gcls; NULL when wtab is already in the workspace) -> dL/dimage.  Shared by the fused step and by the
 // rows backward of the operator API.  `pad` = reflect-padded fp32 image the gradient is taken for.
 template <typename Cfg>
 inline int launch_plane_backward_cfg(const float* pad, int B, int H, int W, const PlaneLists& lists,
@@ -229,7 +228,6 @@ inline int launch_plane_backward_cfg(const float* pad, int B, int H, int W, cons
     fp.pad = pad; fp.Hp = l.pad.Hp; fp.pitch = l.pad.pitch;
     fp.gpart = bp.gpart; fp.wtab = reinterpret_cast<float*>(ws + l.off_wtab);
     fp.slot_map = lists.slot_map; fp.grad = grad_out;
-    fp.wsum = reinterpret_cast<float*>(ws + l.off_wsum);
     fp.B = B; fp.H = H; fp.W = W; fp.HT = l.HT; fp.WT = l.WT; fp.n_parts = BG::NDXG; fp.cap = l.cap;
     const long long npx = (long long)B * H * W;
     auto k = ssg_plane_bwd_kernel<BG>;
@@ -240,9 +238,10 @@ inline int launch_plane_backward_cfg(const float* pad, int B, int H, int W, cons
     }
     {
         StageTimer timer(kStageFinish, st);
-        plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(gcls, lists.counts, l.cap,
-                                                               reinterpret_cast<float*>(ws + l.off_wtab));
-        plane_wsum_kernel<Cfg><<<dim3(l.WT / 16, l.HT / 16, B), 256, 0, st>>>(fp);
+        if (gcls)   // the fused step's row loss has written wtab already
+            plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(gcls, lists.counts, l.cap,
+                                                                   reinterpret_cast<float*>(ws + l.off_wtab));
+        plane_fold_kernel<Cfg><<<dim3(l.WT / 16, l.HT / 16, B), 256, 0, st>>>(fp);
         plane_finish_kernel<Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
     }
     return check_launch("plane_backward", 5);
@@ -262,8 +261,8 @@ inline int launch_plane_step_cfg(const StepInputs& in, int B, int H, int W, int 
     using BG = PlaneBwdGeom<Cfg>;
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
-    const int loss_blocks = 2 * di.sm_count;
-    const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, loss_blocks, grad_sr != nullptr);
+    const int loss_blocks = 2 * di.sm_count;   // two persistent blocks per SM
+    const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, 2 * di.sm_count, grad_sr != nullptr);
     SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
     char* ws = static_cast<char*>(workspace);
     float* pad = reinterpret_cast<float*>(ws + l.off_pad);
@@ -283,22 +282,24 @@ inline int launch_plane_step_cfg(const StepInputs& in, int B, int H, int W, int 
     // rows -> loss terms and dL/dq (in place over q_sr) + per-class sums
     RowLossTParams rp{};
     rp.qs = q_sr; rp.qg = q_gt; rp.slot_pix = lists.slot_pix; rp.counts = lists.counts;
-    rp.cap = l.cap; rp.L = Cfg::L; rp.KS = Cfg::KS; rp.P = Cfg::P; rp.K = Cfg::K;
+    rp.cap = l.cap;
     rp.denom = 3.f * (float)(Cfg::KW * Cfg::KW); rp.sigma = sigma; rp.eps = eps;
     rp.chain = -1.0f / (sigma * 3.f * (float)(Cfg::KW * Cfg::KW));
     rp.mode = rows_mode; rp.want_grad = grad_sr ? 1 : 0; rp.w_l1 = w_l1; rp.w_kl = w_kl;
-    rp.gcls = grad_sr ? reinterpret_cast<float*>(ws + l.off_gcls) : nullptr;
+    rp.wtab = grad_sr ? reinterpret_cast<float*>(ws + l.off_wtab) : nullptr;
     rp.scratch = reinterpret_cast<double*>(ws + l.off_scratch);
-    const size_t rl_smem = (size_t)2 * Cfg::L * kRowTSlots * sizeof(float);
-    SSLB_CUDA(cudaFuncSetAttribute(row_loss_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl_smem));
+    rp.terms = terms;
+    rp.done = reinterpret_cast<unsigned int*>(lists.counts + 4);   // zeroed with the counts, reset by the kernel
+    const size_t rl_smem = (size_t)Cfg::L * kRowTSlots * sizeof(float);
+    auto rl_kernel = w_kl != 0.f ? row_loss_t_kernel<Cfg::KS, Cfg::KW, true> : row_loss_t_kernel<Cfg::KS, Cfg::KW, false>;
+    SSLB_CUDA(cudaFuncSetAttribute(rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl_smem));  // + 21 KB static
     {
         StageTimer timer(kStageRowLoss, st);
-        row_loss_t_kernel<<<loss_blocks, kRowTThreads, rl_smem, st>>>(rp);
-        row_loss_finalize_kernel<<<1, 32, 0, st>>>(rp.scratch, loss_blocks, terms);
+        rl_kernel<<<loss_blocks, kRowTThreads, rl_smem, st>>>(rp);
     }
-    if (int e = check_launch("row_loss_t", 2)) return e;
+    if (int e = check_launch("row_loss_t", 1)) return e;
     if (!grad_sr) return 0;
-    return launch_plane_backward_cfg<Cfg>(pad, B, H, W, lists, l, ws, q_sr, rp.gcls, grad_sr, st);
+    return launch_plane_backward_cfg<Cfg>(pad, B, H, W, lists, l, ws, q_sr, nullptr, grad_sr, st);
 }
 
 // Rows backward behind the reference's operator API (similarity_map / compute_similarity): dL/dq rows in the

@@ -1,11 +1,19 @@
-// Row loss on the offset-major rows of the plane path: qT[d][slot].
+// Row loss on the rows buffers of the plane path (panel layout, plane_geom.cuh: qt_index).
 //
-// One block owns 16 consecutive slots and keeps both of their rows (SR and GT, KS*KS entries each)
-// in shared memory (80 KB: two blocks per SM overlap one block's loads with the other's arithmetic), so the exp / normalise tail of loss_util.py:234-243, the L1 (basic_loss.py:
-// 14-16,59-66) and KL (basic_loss.py:269-282) numerators and the whole adjoint chain down to
-// dL/dq cost one read of each rows buffer and one write (dL/dq overwrites q_sr in place).
-// It also emits, per slot, the sum of dL/dq over every clip class: the weights of the
-// out-of-area terms (similarity.cu:123-124) used by the plane backward.
+// One block owns 16 consecutive slots at a time and keeps both of their rows (SR and GT, KS*KS entries each)
+// in shared memory, so the exp / normalise tail of loss_util.py:234-243, the L1 (basic_loss.py:14-16,59-66)
+// and KL (basic_loss.py:269-282) numerators and the whole adjoint chain down to dL/dq cost one read of
+// each rows buffer and one write (dL/dq overwrites q_sr in place).  It also emits, per slot, the weights of
+// the out-of-area terms (similarity.cu:123-124) used by the plane backward: the sums of dL/dq over the clip
+// classes, folded into one weight per window offset.
+//
+// The kernel is a pure stream over 0.9 GB.  Every thread loads its ~20 entries of both rows straight into
+// registers (40 independent loads in flight, two full 64-byte segments per warp instruction) and keeps them
+// there through the three passes a normalised row needs (row sum, sum of g*s, dL/dq); two blocks per SM overlap
+// one block's loads with the other's arithmetic.  (Measured alternatives, profiles/r02_optimization_log.md:
+// rows round-tripping through shared memory between the passes, and a TMA producer/consumer pipeline with
+// {16 x 128} boxes -- the copy engine handles such 64-byte rows at ~1 per 12 cycles per SM, slower than the
+// load/store units.)
 #pragma once
 
 #include "plane_geom.cuh"
@@ -14,74 +22,83 @@
 namespace sslb {
 
 struct RowLossTParams {
-    float* qs;             // [L][cap] in: q of SR, out: dL/dq (when want_grad)
-    const float* qg;       // [L][cap] q of GT
+    float* qs;             // L x cap (panel layout) in: q of SR, out: dL/dq (when want_grad)
+    const float* qg;       // L x cap q of GT
     const int32_t* slot_pix;
     const int32_t* counts; // counts[0] = slots in use
-    int cap, L, KS, P, K;
+    int cap;
     float denom, sigma, eps, chain;
     int mode, want_grad;
     float w_l1, w_kl;
-    float* gcls;           // [(2K+1)^2][cap] or NULL
-    double* scratch;       // [2 * gridDim.x]
+    float* wtab;           // [cap][KW*KW] out-of-area weight of every window offset, or NULL
+    double* scratch;       // [2 * gridDim.x] block partials
+    double* terms;         // [2] += sum|d|, sum KL (added by the last block to finish, in block order)
+    unsigned int* done;    // block counter, zero before the launch; the last block resets it
 };
 
 constexpr int kRowTThreads = 512;
-constexpr int kRowTSlots = 16;                       // slots per block: 2 rows x 625 x 16 floats = 80 KB => 2 blocks per SM
+constexpr int kRowTSlots = 16;                       // slots per group: 64-byte segments of every offset row
 constexpr int kRowTPhases = kRowTThreads / kRowTSlots;
+static_assert(kRowTSlots == kPanel, "a group of the row loss is one panel of the rows buffers");
 
-__global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams p) {
-    extern __shared__ float rl_smem[];
+// exp(x) for x <= 0 as ex2.approx(x * log2 e): the argument is rounded once (as in the folded division below)
+// and ex2.approx is good to 2^-22, i.e. ~2e-7 relative -- far inside the 1e-5 budget, and 4x fewer
+// instructions than expf in a kernel that is bound by instruction issue.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int KS, int KW, bool HAS_KL>
+__global__ void __launch_bounds__(kRowTThreads, 2) row_loss_t_kernel(RowLossTParams p) {
+    extern __shared__ __align__(16) float gqbuf[];           // [L][NS] dL/dq of the current group (pass 4)
     constexpr int NS = kRowTSlots, NPH = kRowTPhases;
-    const int L = p.L, cap = p.cap, mode = p.mode;
-    float* es = rl_smem;                // [L][NS]
-    float* et = es + L * NS;            // [L][NS]
+    constexpr int L = KS * KS, P = KS / 2, K = KW / 2, NC = 2 * K + 1;
+    const int cap = p.cap, mode = p.mode;
     __shared__ float red[2][NPH][NS];
+    __shared__ float sG[NC * NC][NS], sT[NC * KW][NS], sR[NC][NS], sW[NS * KW * KW];
     __shared__ double dred[32];
-    const int s = threadIdx.x % NS, ph = threadIdx.x / NS;
+    __shared__ int last_flag;
     const int n_slots = min(p.counts[0], cap);
-    const float nscale = -1.0f / (p.denom * p.sigma);
+    const int n_groups = (n_slots + NS - 1) / NS;
+    const int s = threadIdx.x % NS, ph = threadIdx.x / NS;
+    // e = exp(-1 * (q / (C kw^2)) / sigma) of loss_util.py:224-225 as 2^(q * nscale2): the two divisions and the
+    // change of base are folded into one constant (computed in double), so the argument is rounded once
+    const float nscale2 = (float)(-1.4426950408889634 / ((double)p.denom * (double)p.sigma));
     const float w_l1 = p.w_l1, w_kl = p.w_kl, chain = p.chain, eps = p.eps;
-    const long long gstride = (long long)NPH * cap;   // global stride between this thread's offsets
+    constexpr int gstride = NPH * kPanel;             // global stride between this thread's offsets (panel layout)
     constexpr int sstride = NPH * NS;                 // shared stride
-    const int n_mine = (L - ph + NPH - 1) / NPH;      // offsets d = ph, ph + NPH, ... handled by this thread
+    constexpr int NFULL = L / NPH;                    // every thread handles offsets d = ph + NPH * i, i < NFULL,
+    const bool has_tail = ph < L - NFULL * NPH;       // and the first L mod NPH phases one more
+    constexpr int NV = NFULL + 1;
     double l1_tot = 0.0, kl_tot = 0.0;
-    for (int slot0 = blockIdx.x * NS; slot0 < n_slots; slot0 += gridDim.x * NS) {
-        const int slot = slot0 + s;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int slot = g * NS + s;
         const bool valid = slot < n_slots && p.slot_pix[slot] >= 0;
-        // pass 1: e = exp(-1 * (q / (C kw^2)) / sigma), partial row sums.  Loads are issued in batches
-        // of 2*UN so that enough bytes are in flight to cover the HBM latency.
-        float zs = 0.f, zt = 0.f;
-        constexpr int UN = 8;
+        // The thread's ~20 (slot, offset) pairs are loaded straight into registers -- 2 * NV independent loads in
+        // flight per thread, every warp instruction two full 64-byte segments -- and stay there through all
+        // passes; shared memory only carries the row reductions and dL/dq for the class sums of pass 4.
+        float vs[NV], vt[NV];
         {
-            const float* gs = p.qs + (long long)ph * cap + slot;
-            const float* gg = p.qg + (long long)ph * cap + slot;
-            float* ps = es + ph * NS + s;
-            float* pt = et + ph * NS + s;
-            for (int i0 = 0; i0 < n_mine; i0 += UN) {
-                float qa[UN], qb[UN];
+            const float* gs = p.qs + qt_index(ph, slot, L);   // the group is one panel: L * 64 contiguous bytes
+            const float* gg = p.qg + qt_index(ph, slot, L);
 #pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const bool ok = valid && i0 + u < n_mine;
-                    qa[u] = ok ? __ldcs(gs + u * gstride) : 0.f;
-                    qb[u] = ok ? __ldcs(gg + u * gstride) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    if (i0 + u < n_mine) {
-                        // exp(-1 * (q / (C kw^2)) / sigma) of loss_util.py:224-225; the two divisions are folded
-                        // into one multiplication (<= 1.5 ulp of the argument, the size of q's own rounding)
-                        const float a = valid ? expf(qa[u] * nscale) : 0.f;
-                        const float b = valid ? expf(qb[u] * nscale) : 0.f;
-                        ps[u * sstride] = a;
-                        pt[u * sstride] = b;
-                        zs += a;
-                        zt += b;
-                    }
-                }
-                gs += UN * gstride; gg += UN * gstride;
-                ps += UN * sstride; pt += UN * sstride;
+            for (int i = 0; i < NV; ++i) {
+                const bool on = valid && (i < NFULL || has_tail);
+                vs[i] = on ? __ldcs(gs + i * gstride) : 0.f;
+                vt[i] = on ? __ldcs(gg + i * gstride) : 0.f;
             }
+        }
+        // pass 1: e, partial row sums
+        float zs = 0.f, zt = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const bool on = valid && (i < NFULL || has_tail);
+            vs[i] = on ? ex2_approx(vs[i] * nscale2) : 0.f;
+            vt[i] = on ? ex2_approx(vt[i] * nscale2) : 0.f;
+            zs += vs[i];
+            zt += vt[i];
         }
         red[0][ph][s] = zs;
         red[1][ph][s] = zt;
@@ -94,29 +111,28 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
             rs = 1.0f / (a + eps);
             rt = 1.0f / (b + eps);
         }
-        __syncthreads();
-        // pass 2: rows, loss terms, dL/drow; es <- s, et <- g
+        // pass 2: rows, loss terms, dL/drow; vs <- s, vt <- g
         float l1 = 0.f, kl = 0.f, dot = 0.f;
-        {
-            float* ps = es + ph * NS + s;
-            float* pt = et + ph * NS + s;
-            for (int i = 0; i < n_mine; ++i, ps += sstride, pt += sstride) {
-                const float sv = rs * *ps, tv = rt * *pt;
-                const float df = sv - tv;
-                l1 += fabsf(df);
-                float g = df > 0.f ? w_l1 : (df < 0.f ? -w_l1 : 0.f);
-                if (w_kl != 0.f) {
-                    const float sc = fmaxf(sv, 1e-10f), tc = fmaxf(tv, 1e-10f);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float sv = rs * vs[i], tv = rt * vt[i];
+            const float df = sv - tv;
+            l1 += fabsf(df);
+            float gg = df > 0.f ? w_l1 : (df < 0.f ? -w_l1 : 0.f);
+            if (HAS_KL) {
+                const bool on = valid && (i < NFULL || has_tail);
+                const float sc = fmaxf(sv, 1e-10f), tc = fmaxf(tv, 1e-10f);
+                if (on) {
                     kl += kl_term(sc, tc) + (mode == SSL_B200_ROWS_NORM ? ((tc - tv) - (sc - sv)) : (tc - sc));
-                    if (sv > 1e-10f) g -= w_kl * tc / sc;
+                    if (sv > 1e-10f) gg -= w_kl * tc / sc;
                 }
-                if (!valid) g = 0.f;
-                dot = fmaf(g, sv, dot);
-                *ps = sv;
-                *pt = g;
             }
+            dot = fmaf(gg, sv, dot);
+            vs[i] = sv;
+            vt[i] = gg;
         }
         if (valid) { l1_tot += (double)l1; kl_tot += (double)kl; }
+        __syncthreads();            // every thread has read red (row sums) before it is reused
         if (p.want_grad) {
             red[0][ph][s] = dot;
             __syncthreads();
@@ -127,21 +143,28 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
             }
             // pass 3: dL/dq = chain * s * (g - sum_m g_m s_m)   (EXP rows: chain * e * g)
             {
-                float* ps = es + ph * NS + s;
-                const float* pt = et + ph * NS + s;
-                float* gs = p.qs + (long long)ph * cap + slot;
+                float* pw = gqbuf + ph * NS + s;
+                float* gs = p.qs + qt_index(ph, slot, L);
                 const bool store = slot < n_slots;
-                for (int i = 0; i < n_mine; ++i, ps += sstride, pt += sstride, gs += gstride) {
-                    const float gq = chain * *ps * (*pt - dsum);
-                    *ps = gq;
-                    if (store) *gs = gq;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    if (i < NFULL || has_tail) {
+                        const float gq = chain * vs[i] * (vt[i] - dsum);
+                        pw[i * sstride] = gq;
+                        if (store) gs[i * gstride] = gq;
+                    }
                 }
             }
             __syncthreads();
-            // pass 4: per clip class sums of dL/dq (classes with nothing out of area are skipped)
-            if (p.gcls && slot < n_slots) {
-                const int K = p.K, P = p.P, KS = p.KS;
-                const int NC = 2 * K + 1, U = P - K;
+            // pass 4: weights of the out-of-area terms (similarity.cu:123-124: where the neighbour counts as
+            // zero only the centre pixel gets 2*I*g).
+            //  (a) sG[class][slot] = sum of dL/dq over the offsets of a clip class (classes with nothing out of
+            //      area stay zero);
+            //  (b) wtab[slot][(a,b)] = sum of sG over the classes for which window offset (a,b) is out of area:
+            //      sums over the column classes first (sR: whole row class out, sT: column b out), then over
+            //      the row classes.  Rows of 16 slots are contiguous in wtab: written as one coalesced block.
+            if (p.wtab) {
+                constexpr int U = P - K;
                 for (int c = ph; c < NC * NC; c += NPH) {
                     const int ca = c / NC, cb = c % NC;
                     float acc = 0.f;
@@ -151,21 +174,78 @@ __global__ void __launch_bounds__(kRowTThreads) row_loss_t_kernel(RowLossTParams
                         const int dx0 = cb < K ? cb - P : (cb > K ? U + (cb - K) : -U);
                         const int dx1 = cb == K ? U : dx0;
                         for (int dy = dy0; dy <= dy1; ++dy) {
-                            const float* row = es + ((dy + P) * KS + dx0 + P) * NS + s;
+                            const float* row = gqbuf + ((dy + P) * KS + dx0 + P) * NS + s;
                             for (int dx = dx0; dx <= dx1; ++dx, row += NS) acc += *row;
                         }
                     }
-                    p.gcls[(long long)c * cap + slot] = acc;
+                    sG[c][s] = acc;
+                }
+                __syncthreads();
+                for (int i = ph; i < NC * KW; i += NPH) {          // sT[ca][b]: column b of the window out of class cb
+                    const int ca = i / KW, b = i % KW - K;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int cb = 0; cb < NC; ++cb)
+                        if (b < class_lo(cb, K) || b > class_hi(cb, K)) acc += sG[ca * NC + cb][s];
+                    sT[i][s] = acc;
+                }
+                if (ph < NC) {                                      // sR[ca]: everything of row class ca
+                    float acc = 0.f;
+#pragma unroll
+                    for (int cb = 0; cb < NC; ++cb) acc += sG[ph * NC + cb][s];
+                    sR[ph][s] = acc;
+                }
+                __syncthreads();
+                for (int i = ph; i < KW * KW; i += NPH) {
+                    const int a = i / KW - K, b = i % KW;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int ca = 0; ca < NC; ++ca)
+                        acc += (a < class_lo(ca, K) || a > class_hi(ca, K)) ? sR[ca][s] : sT[ca * KW + b][s];
+                    sW[s * (KW * KW) + i] = acc;
+                }
+                __syncthreads();
+                {
+                    const int n_here = min(NS, n_slots - g * NS);
+                    float* dst = p.wtab + (long long)g * NS * (KW * KW);
+                    for (int i = threadIdx.x; i < n_here * KW * KW; i += kRowTThreads) dst[i] = sW[i];
                 }
             }
         }
-        __syncthreads();
     }
-    l1_tot = block_sum(l1_tot, dred);
-    kl_tot = block_sum(kl_tot, dred);
-    if (threadIdx.x == 0) {
-        p.scratch[2 * blockIdx.x] = l1_tot;
-        p.scratch[2 * blockIdx.x + 1] = kl_tot;
+    // block partials (fixed reduction tree) -> scratch
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        l1_tot = warp_sum(l1_tot);
+        kl_tot = warp_sum(kl_tot);
+        __syncthreads();
+        if (lane == 0) { dred[warp] = l1_tot; dred[16 + warp] = kl_tot; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0, b = 0.0;
+            for (int w = 0; w < kRowTThreads / 32; ++w) { a += dred[w]; b += dred[16 + w]; }
+            p.scratch[2 * blockIdx.x] = a;
+            p.scratch[2 * blockIdx.x + 1] = b;
+            __threadfence();
+            last_flag = atomicAdd(p.done, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        // the last block to finish adds all partials in block order => bitwise reproducible loss
+        if (last_flag && threadIdx.x < 32) {
+            __threadfence();
+            double a = 0.0, b = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) {
+                a += __ldcg(p.scratch + 2 * i);
+                b += __ldcg(p.scratch + 2 * i + 1);
+            }
+            a = warp_sum(a);
+            b = warp_sum(b);
+            if (threadIdx.x == 0) {
+                p.terms[0] += a;
+                p.terms[1] += b;
+                *p.done = 0u;
+            }
+        }
     }
 }
 

@@ -26,7 +26,7 @@ namespace sslb {
 #ifdef SSLB_EXPERIMENT_NOGQ   // timing experiment only: how much of the kernel is the dL/dq gather?
 #define SSLB_GQ(gq, packed) (1e-9f * (float)((packed) & 1023))
 #else
-#define SSLB_GQ(gq, packed) __ldg((gq) + ((packed) >> 8))
+#define SSLB_GQ(gq, packed) __ldg(gq_at<Cfg>(gq, packed))
 #endif
 
 template <typename Cfg>
@@ -61,7 +61,7 @@ struct PlaneBwdCfg {
 };
 
 struct PlaneBwdParams {
-    const float* gqT;         // [L][cap]
+    const float* gqT;         // L x cap, panel layout (qt_index)
     const int32_t* tile_cols; // [n_btiles][RCOLS+1] column starts inside the tile's entry list
     const uint8_t* tile_cum;  // [n_btiles][RCOLS][CUM_PITCH] entries of the column above region row rr
     const int32_t* tile_ent;  // [n_btiles][LIST_STRIDE] (slot << 8) | region row
@@ -144,12 +144,19 @@ __device__ __forceinline__ void place_offsets(int kind, int dy, int& lo_off, int
     hi_off = kind == 0 ? -P + ahi : -P - dy - alo;
 }
 
-// row of gqT an entry's value comes from: kind 0 reads offset d, kind 1 the mirrored offset -d
+// where an entry's value comes from: kind 0 reads offset d, kind 1 the mirrored offset -d.  Returns gqT advanced to
+// the offset's 64-byte segment of panel 0; gq_at() adds the slot's panel and lane.
 template <typename Cfg>
 __device__ __forceinline__ const float* place_source(const PlaneBwdParams& p, int kind, int dy, int dx) {
     constexpr int P = Cfg::P;
     const int d = kind == 0 ? (dy + P) * Cfg::KS + dx + P : (-dy + P) * Cfg::KS + (-dx) + P;
-    return p.gqT + (long long)d * p.cap;
+    return p.gqT + d * kPanel;
+}
+
+template <typename Cfg>
+__device__ __forceinline__ const float* gq_at(const float* gq, int packed) {
+    const int slot = packed >> 8;
+    return gq + (long long)(slot >> 4) * (Cfg::L * kPanel) + (slot & (kPanel - 1));
 }
 
 template <typename Cfg, int NB>
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(256) plane_rows_to_slots_kernel(const float* r
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
         const bool real = slot_pix[slot] >= 0;
         const float* src = rows + (long long)(real ? slot_ref[slot] : 0) * L;
-        for (int d = 0; d < L; ++d) gqT[(long long)d * cap + slot] = real ? __ldg(src + d) : 0.f;
+        for (int d = 0; d < L; ++d) gqT[qt_index(d, slot, L)] = real ? __ldg(src + d) : 0.f;
     }
 }
 
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(256) plane_class_sums_kernel(const float* gqT,
             const int dy0 = ca < K ? ca - P : (ca > K ? U + (ca - K) : -U), dy1 = ca == K ? U : dy0;
             const int dx0 = cb < K ? cb - P : (cb > K ? U + (cb - K) : -U), dx1 = cb == K ? U : dx0;
             for (int dy = dy0; dy <= dy1; ++dy)
-                for (int dx = dx0; dx <= dx1; ++dx) acc += gqT[(long long)((dy + P) * KS + dx + P) * cap + slot];
+                for (int dx = dx0; dx <= dx1; ++dx) acc += gqT[qt_index((dy + P) * KS + dx + P, slot, KS * KS)];
         }
         gcls[(long long)c * cap + slot] = acc;
     }
@@ -542,18 +549,19 @@ __global__ void __launch_bounds__(256) plane_class_sums_kernel(const float* gqT,
 struct PlaneFinishParams {
     const float* pad;         // [B][3][Hp][pitch] reflect-padded fp32 SR (image 0 of the padded buffer)
     int Hp, pitch;
-    const float* gpart;       // [NDXG][B][3][HT][WT]
+    float* gpart;             // [NDXG][B][3][HT][WT]; part 0 is overwritten with the folded padded gradient
     const float* wtab;        // [cap][KW*KW]
     const int32_t* slot_map;
-    float* wsum;              // [B][HT][WT] out-of-area weight of every padded pixel
     float* grad;              // [B,3,H,W], overwritten
     int B, H, W, HT, WT, n_parts, cap;
 };
 
-// wsum(Y,X) = sum over the edge pixels p = (Y,X) - (a,b), |a|,|b| <= K, of wtab[p][(a,b)].
-// One block = 16x16 padded pixels; the slots of the (16+2K)^2 pixels around it are staged once.
+// Fold of the padded-domain gradient, one block = 16x16 padded pixels of one image:
+//   wsum(Y,X) = sum over the edge pixels p = (Y,X) - (a,b), |a|,|b| <= K, of wtab[p][(a,b)]   (the slots of the
+//               (16+2K)^2 pixels around the block are staged once)
+//   G(Y,X,c)  = sum of the dx-group partials + 2 * wsum * I(Y,X,c)        -> written over part 0
 template <typename Cfg>
-__global__ void __launch_bounds__(256) plane_wsum_kernel(PlaneFinishParams p) {
+__global__ void __launch_bounds__(256) plane_fold_kernel(PlaneFinishParams p) {
     constexpr int P = Cfg::P, K = Cfg::K, KW = Cfg::KW, T = 16, R = T + 2 * K;
     __shared__ int32_t ss[R][R + 1];
     const int b = blockIdx.z, Y0 = blockIdx.y * T, X0 = blockIdx.x * T;
@@ -579,28 +587,21 @@ __global__ void __launch_bounds__(256) plane_wsum_kernel(PlaneFinishParams p) {
                 if (slot >= 0) w += p.wtab[(long long)slot * (KW * KW) + (a + K) * KW + bb + K];
             }
     }
-    p.wsum[((long long)b * p.HT + Y0 + ty) * p.WT + X0 + tx] = w;
-}
-
-// Padded-domain gradient at (Y,X) of image b, all three channels.
-template <typename Cfg>
-__device__ __forceinline__ void padded_grad_at(const PlaneFinishParams& p, int b, int Y, int X, float (&g)[3]) {
+    const int Y = Y0 + ty, X = X0 + tx;
     const long long plane = (long long)p.HT * p.WT;
+    const bool inside = Y < p.Hp && X < p.W + 2 * P;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+        const long long o = ((long long)b * 3 + c) * plane + (long long)Y * p.WT + X;
         float s = 0.f;
-        for (int part = 0; part < p.n_parts; ++part)
-            s += p.gpart[(((long long)part * p.B + b) * 3 + c) * plane + (long long)Y * p.WT + X];
-        g[c] = s;
+        for (int part = 0; part < p.n_parts; ++part) s += p.gpart[(long long)part * p.B * 3 * plane + o];
+        if (inside) s = fmaf(2.f * w, __ldg(p.pad + (((long long)b * 3 + c) * p.Hp + Y) * p.pitch + X), s);
+        p.gpart[o] = s;
     }
-    const float wsum = p.wsum[(long long)b * plane + (long long)Y * p.WT + X];
-    const float* ip = p.pad + (long long)b * 3 * p.Hp * p.pitch + (long long)Y * p.pitch + X;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) g[c] = fmaf(2.f * wsum, __ldg(ip + (long long)c * p.Hp * p.pitch), g[c]);
 }
 
-// Adjoint of F.pad(reflect) (similaritywrapper.py:64) as a gather: an image pixel sums the padded
-// pixels that mirror onto it (at most 2 per axis).
+// Adjoint of F.pad(reflect) (similaritywrapper.py:64) as a gather: an image pixel sums the padded pixels that
+// mirror onto it (at most 3 per axis).
 template <typename Cfg>
 __global__ void __launch_bounds__(256) plane_finish_kernel(PlaneFinishParams p) {
     constexpr int P = Cfg::P;
@@ -614,12 +615,14 @@ __global__ void __launch_bounds__(256) plane_finish_kernel(PlaneFinishParams p) 
     if (y <= p.H - 2 && y >= p.H - 1 - P) Ys[ny++] = P + 2 * (p.H - 1) - y;
     if (x >= 1 && x <= P) Xs[nx++] = P - x;
     if (x <= p.W - 2 && x >= p.W - 1 - P) Xs[nx++] = P + 2 * (p.W - 1) - x;
+    const long long plane = (long long)p.HT * p.WT;
+    const float* G = p.gpart + (long long)b * 3 * plane;
     float tot[3] = {0.f, 0.f, 0.f};
     for (int iy = 0; iy < ny; ++iy)
         for (int ix = 0; ix < nx; ++ix) {
-            float g[3];
-            padded_grad_at<Cfg>(p, b, Ys[iy], Xs[ix], g);
-            tot[0] += g[0]; tot[1] += g[1]; tot[2] += g[2];
+            const long long o = (long long)Ys[iy] * p.WT + Xs[ix];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tot[c] += G[c * plane + o];
         }
 #pragma unroll
     for (int c = 0; c < 3; ++c) p.grad[((long long)b * 3 + c) * hw + rem] = tot[c];

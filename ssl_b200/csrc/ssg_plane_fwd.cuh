@@ -24,7 +24,7 @@ namespace sslb {
 struct PlaneFwdParams {
     const float* pad;        // [2][B][3][Hp][pitch] reflect-padded fp32 images (pad.cuh); image 0 = SR, 1 = GT
     int Hp, pitch;
-    float* qT[2];            // [KS*KS][cap]
+    float* qT[2];            // KS*KS x cap, panel layout (qt_index)
     const float* eout[2];    // [cap][NCLS*NCLS]
     PlaneLists lists;
     PlaneGeom g;
@@ -33,35 +33,54 @@ struct PlaneFwdParams {
 
 // ---- Eout tables -------------------------------------------------------------------------
 // eout[slot][ca*NCLS+cb] = sum over window offsets (a,b) outside A(ca) x A(cb) of sum_c I(p+(a,b))^2.
-// One warp per slot.  The complement of a clip range is a prefix or a suffix of the window, so every
-// entry is a sum of at most two running sums (all terms non-negative, no subtraction).
+// One block per unit (8 columns x TYF rows of edge-pixel positions): the squared norms E2 = sum_c I^2 of the
+// unit's (TYF + 2K) x (8 + 2K) neighbourhood are formed once in shared memory and shared by all of its slots
+// (every E2 value serves up to (2K+1)^2 of them); then one warp per slot.  The complement of a clip range is
+// a prefix or a suffix of the window, so every entry is a sum of at most two running sums (all terms
+// non-negative, no subtraction).
 template <typename Cfg>
 __global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
     constexpr int K = Cfg::K, KW = Cfg::KW, NC = Cfg::NCLS, NW = KW * KW, P = Cfg::P;
-    // sOut[a][m]: sum of the first m (m <= K) window columns of row a; sOut[a][K+1+m]: of the last m; sFull[a]: all
+    constexpr int ER = Cfg::ROWS, EC = 8 + 2 * K, EP = EC + 1;   // region rows, columns, pitch
+    __shared__ float sE2[ER * EP];
     __shared__ float sE[4][NW], sPre[4][KW][K + 1], sSuf[4][KW][K + 1], sFull[4][KW];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_slots = min(p.lists.counts[0], p.cap);
-    const int H = p.g.H, W = p.g.W;
+    const int u = blockIdx.x, which = blockIdx.y;
+    const int slot0 = p.lists.unit_start[u], slot1 = min(p.lists.unit_start[u + 1], p.cap);
+    if (slot0 >= slot1) return;
+    int b, ty, tx, cx;
+    decode_unit(p.g, u, b, ty, tx, cx);
+    // padded coordinates of region (0,0): image (ty*TYF - K, tx*TXF + cx*8 - xs - K)
+    const int Y0 = ty * Cfg::TYF - K + P, X0 = tx * Cfg::TXF + cx * 8 - p.g.xs - K + P;
+    const int Wp = p.g.W + 2 * P;
     const long long plane = (long long)p.Hp * p.pitch;
-    for (int slot = blockIdx.x * 4 + w; slot < n_slots; slot += gridDim.x * 4) {
-        const int pix = p.lists.slot_pix[slot];
-        float* out = const_cast<float*>(p.eout[blockIdx.y]) + (long long)slot * (NC * NC);
-        if (pix < 0) {
+    const float* img = p.pad + ((long long)which * p.g.B + b) * 3 * plane;
+    for (int i = threadIdx.x; i < ER * EC; i += blockDim.x) {
+        const int ry = i / EC, rx = i - ry * EC;
+        const int Y = Y0 + ry, X = X0 + rx;
+        float e = 0.f;
+        if (Y >= 0 && Y < p.Hp && X >= 0 && X < Wp) {
+            const float* q = img + (long long)Y * p.pitch + X;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = __ldg(q + c * plane);
+                e = fmaf(v, v, e);
+            }
+        }
+        sE2[ry * EP + rx] = e;
+    }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int slot = slot0 + w; slot < slot1; slot += 4) {
+        const int rc = p.lists.slot_rc[slot];
+        float* out = const_cast<float*>(which ? p.eout[1] : p.eout[0]) + (long long)slot * (NC * NC);
+        if (rc < 0) {
             for (int i = lane; i < NC * NC; i += 32) out[i] = 0.f;
             continue;
         }
-        const int hw = H * W, b = pix / hw, rem = pix - b * hw, y = rem / W, x = rem - y * W;
-        const float* img = p.pad + ((long long)blockIdx.y * p.g.B + b) * 3 * plane + (long long)(y + P) * p.pitch + x + P;
+        const int re = rc >> 8, lx = (rc & 255) & 7;   // row lane (tile row + K), column inside the unit
         for (int i = lane; i < NW; i += 32) {
-            const int a = i / KW - K, bb = i % KW - K;
-            float e = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v = __ldg(img + c * plane + a * p.pitch + bb);
-                e = fmaf(v, v, e);
-            }
-            sE[w][i] = e;
+            const int a = i / KW, bb = i % KW;         // window offset (a - K, bb - K)
+            sE[w][i] = sE2[(re - K + a) * EP + lx + bb];
         }
         __syncwarp();
         if (lane < KW) {  // one window row per lane: running sums from the left and from the right
@@ -276,7 +295,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
         const int ca = clip_class(dy, P, K);
         const bool clipped = ca != K || cb != K;
         const int cls = ca * NC + cb;
-        const long long qrow = (long long)((dy + P) * Cfg::KS + g_dx + P) * cap;
+        const int qd = (dy + P) * Cfg::KS + g_dx + P;   // offset index of this thread's plane
 
         BoxCarry carry[GJ];
 #pragma unroll
@@ -342,7 +361,7 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
                             out[e] = rcs[e] >= 0 ? t[0] + eo[e] : 0.f;
                         }
                     }
-                    *reinterpret_cast<float4*>(qT + qrow + gs) = make_float4(out[0], out[1], out[2], out[3]);
+                    *reinterpret_cast<float4*>(qT + qt_index(qd, gs, Cfg::L)) = make_float4(out[0], out[1], out[2], out[3]);
                 }
             }
             worker_sync<Cfg::ROWS>(wp);
@@ -397,7 +416,7 @@ constexpr size_t plane_fwd_smem_bytes() {
            (size_t)Cfg::RC_SMEM * sizeof(int32_t);
 }
 
-// qT[d][slot] -> rows[i][d] in the reference's row order (i = position in the flat edge list).
+// rows buffer (panel layout) -> rows[i][d] in the reference's row order (i = position in the flat edge list).
 __global__ void __launch_bounds__(256) plane_rows_to_reference_kernel(const float* qT, int cap, const int32_t* edges,
                                                                       const int32_t* n_edges_dev, int max_edges,
                                                                       const int32_t* slot_map, int L, float* rows) {
@@ -405,7 +424,7 @@ __global__ void __launch_bounds__(256) plane_rows_to_reference_kernel(const floa
     for (int n = blockIdx.x; n < mc; n += gridDim.x) {
         const int slot = slot_map[edges[n]];
         for (int d = threadIdx.x; d < L; d += blockDim.x)
-            rows[(long long)n * L + d] = slot >= 0 && slot < cap ? qT[(long long)d * cap + slot] : 0.f;
+            rows[(long long)n * L + d] = slot >= 0 && slot < cap ? qT[qt_index(d, slot, L)] : 0.f;
     }
 }
 

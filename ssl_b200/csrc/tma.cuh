@@ -54,6 +54,26 @@ inline int make_plane_map(CUtensorMap* map, const float* base, int n_planes, int
     return 0;
 }
 
+// fp32 matrix [rows][pitch] (pitch in elements, a multiple of 4; `cols` of them valid) as a 2-D tensor;
+// box = {box_cols, box_rows}; out-of-bounds elements read as zero.
+inline int make_matrix_map(CUtensorMap* map, const float* base, int rows, int cols, int pitch, int box_cols,
+                           int box_rows) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return fail(SSL_B200_ENOTSUP, "cuTensorMapEncodeTiled is not available from this driver");
+    SSLB_REQUIRE(pitch % 4 == 0 && box_cols % 4 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0,
+                 "tensor map needs 16-byte aligned rows");
+    SSLB_REQUIRE(box_cols <= 256 && box_rows <= 256, "tensor map box too large");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SSL_B200_EINVAL, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
 // ---- device side ---------------------------------------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
