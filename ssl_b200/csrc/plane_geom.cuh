@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(256) plane_units_emit_kernel(PlaneListParams p
             const int re = yy + ly + p.g.K, ex = cx * 8 + lx;
             s_rc[wib][t] = (re << 8) | ex;
             s_pix[wib][t] = (b * p.g.H + y) * p.g.W + x;
-            s_h[wib][t] = (uint8_t)((srp * re + ex) & 31);
+            // sort key: the shared-memory bank of the slot in the forward ring, or (kSpreadRows == 0) the column
+            s_h[wib][t] = kSpreadRows > 0 ? (uint8_t)((srp * re + ex) & 31) : (uint8_t)lx;
         }
         n += __popc(ball);
     }
@@ -240,13 +241,15 @@ __global__ void __launch_bounds__(256) plane_units_emit_kernel(PlaneListParams p
     int rank = incl - cnt;
     // 3. rank -> position: ranks laid out in kSpreadRows rows of m, read column by column, dealt to the
     //    4-slot groups round-robin (position = 4 * group + index in group)
-    const int m = (n + kSpreadRows - 1) / kSpreadRows, nfull = n / m, part = n % m;
+    const int ksr = kSpreadRows > 0 ? kSpreadRows : 1;
+    const int m = (n + ksr - 1) / ksr, nfull = n / m, part = n % m;
     const int gtot = ((n + 3) & ~3) / 4;
     for (int t = 0; t < n; ++t) {
         if (s_h[wib][t] != lane) continue;
         const int rr = rank / m, cc = rank % m;
         const int f = cc * nfull + (cc < part ? cc : part) + rr;
-        const int slot = start + 4 * (f % gtot) + f / gtot;
+        // kSpreadRows == 0: column-major order inside the unit (the entries of an image column are consecutive slots)
+        const int slot = kSpreadRows > 0 ? start + 4 * (f % gtot) + f / gtot : start + rank;
         ++rank;
         if (slot < p.capacity) {
             p.out.slot_pix[slot] = s_pix[wib][t];
