@@ -75,6 +75,27 @@ __global__ void __launch_bounds__(kElThreads) edge_count_kernel(EdgeListParams p
     }
 }
 
+// Number of edge pixels only (the host entry sizes its workspace from it): total[0] += count.
+__global__ void __launch_bounds__(kElThreads) mask_count_kernel(EdgeListParams p, int32_t* total) {
+    __shared__ int red[32];
+    int local = 0;
+    for (long long flat = (long long)blockIdx.x * kElThreads + threadIdx.x; flat < p.n_pixels;
+         flat += (long long)gridDim.x * kElThreads) {
+        int b = 0;
+        local += is_edge_pixel(p, flat, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t = threadIdx.x < kElThreads / 32 ? red[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0 && t) atomicAdd(total, t);
+    }
+}
+
 // One block: exclusive scan of chunk_counts -> chunk_offsets, totals -> counts[0..1].
 __global__ void __launch_bounds__(1024) edge_scan_kernel(EdgeListParams p) {
     __shared__ int warp_tot[32];

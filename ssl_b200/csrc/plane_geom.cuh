@@ -143,13 +143,14 @@ __device__ __forceinline__ bool mask_is_edge(const float* mask, int mask_channel
 __global__ void __launch_bounds__(256) plane_mark_edges_kernel(PlaneListParams p) {
     const int mc = edge_count(p.n_edges_dev, p.max_edges);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc; i += gridDim.x * blockDim.x)
-        p.out.slot_map[p.edges[i]] = -2;
+        if (p.edges[i] >= 0) p.out.slot_map[p.edges[i]] = -2;
 }
 
 // slot_ref[slot] = position of the slot's pixel in the flat edge list (after the unit passes)
 __global__ void __launch_bounds__(256) plane_slot_ref_kernel(PlaneListParams p, int32_t* slot_ref) {
     const int mc = edge_count(p.n_edges_dev, p.max_edges);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mc; i += gridDim.x * blockDim.x) {
+        if (p.edges[i] < 0) continue;
         const int slot = p.out.slot_map[p.edges[i]];
         if (slot >= 0 && slot < p.capacity) slot_ref[slot] = i;
     }

@@ -108,6 +108,7 @@ inline PadLayout pad_layout(int B, int H, int W, int P) {
     return l;
 }
 
+// Pads img0 (and img1 right behind it when given) into `out`.
 inline int launch_pad(const void* img0, int dtype0, const void* img1, int dtype1, int B, int H, int W, int P,
                       float* out, cudaStream_t st) {
     DeviceInfo di;
@@ -123,9 +124,11 @@ inline int launch_pad(const void* img0, int dtype0, const void* img1, int dtype1
     return check_launch("pad_images");
 }
 
+// img_first / n_img: which of the (up to two) padded image sets this launch covers (0 = SR, 1 = GT).
 template <typename Cfg>
 inline int launch_plane_forward_cfg(const float* pad, int n_img, const PlaneGeom& g, const PlaneLists& lists, int cap,
-                                    float* qT, float* qT2, float* eout, float* eout2, cudaStream_t st) {
+                                    float* qT, float* qT2, float* eout, float* eout2, cudaStream_t st,
+                                    int img_first = 0, int n_pad_sets = -1) {
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
     const PadLayout pl = pad_layout(g.B, g.H, g.W, Cfg::P);
@@ -139,7 +142,9 @@ inline int launch_plane_forward_cfg(const float* pad, int n_img, const PlaneGeom
     const int tiles = g.B * g.nty * g.ntx;
     CUtensorMap tmap;
     // both image sets are one contiguous stack of n_img * B * 3 planes
-    if (int e = make_plane_map(&tmap, pad, n_img * g.B * 3, pl.Hp, pl.Wp, pl.pitch, Cfg::IPITCH, Cfg::IROWS, 3)) return e;
+    if (n_pad_sets < 0) n_pad_sets = n_img;
+    p.img_first = img_first;
+    if (int e = make_plane_map(&tmap, pad, n_pad_sets * g.B * 3, pl.Hp, pl.Wp, pl.pitch, Cfg::IPITCH, Cfg::IROWS, 3)) return e;
     {
         StageTimer timer(kStageEout, st);
         plane_eout_kernel<Cfg><<<dim3(g.n_units, n_img), 128, 0, st>>>(p);
@@ -203,6 +208,7 @@ inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int
 
 // dL/dq (offset-major, gqT) + per-class sums (gcls; NULL when wtab is already in the workspace) -> dL/dimage.  Shared by the fused step and by the
 // rows backward of the operator API.  `pad` = reflect-padded fp32 image the gradient is taken for.
+// grad_out == NULL: stop after the fold -- the padded-domain gradient stays in part 0 of gpart (ws + l.off_gpart).
 template <typename Cfg>
 inline int launch_plane_backward_cfg(const float* pad, int B, int H, int W, const PlaneLists& lists,
                                      const PlaneStepLayout& l, char* ws, const float* gqT, const float* gcls,
@@ -246,7 +252,7 @@ inline int launch_plane_backward_cfg(const float* pad, int B, int H, int W, cons
             plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(gcls, lists.counts, l.cap,
                                                                    reinterpret_cast<float*>(ws + l.off_wtab));
         plane_fold_kernel<Cfg><<<dim3(l.WT / 16, l.HT / 16, B), 256, 0, st>>>(fp);
-        plane_finish_kernel<Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
+        if (grad_out) plane_finish_kernel<Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
     }
     return check_launch("plane_backward", 5);
 }
@@ -256,6 +262,7 @@ struct StepInputs {
     const void* sr; const void* gt; int dtype_sr, dtype_gt;
     const float* mask; int mask_channels, mask_stride;     // mask == NULL: use edges
     const int32_t* edges; const int32_t* n_edges_dev;
+    cudaEvent_t gt_ready;   // optional: GT is still arriving (host entry); the SR half of the forward runs before it
 };
 
 template <typename Cfg>
@@ -270,7 +277,12 @@ inline int launch_plane_step_cfg(const StepInputs& in, int B, int H, int W, int 
     SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
     char* ws = static_cast<char*>(workspace);
     float* pad = reinterpret_cast<float*>(ws + l.off_pad);
-    if (int e = launch_pad(in.sr, in.dtype_sr, in.gt, in.dtype_gt, B, H, W, Cfg::P, pad, st)) return e;
+    float* pad_gt = pad + l.pad.bytes_per_image_set / sizeof(float);
+    if (in.gt_ready) {
+        if (int e = launch_pad(in.sr, in.dtype_sr, nullptr, in.dtype_sr, B, H, W, Cfg::P, pad, st)) return e;
+    } else {
+        if (int e = launch_pad(in.sr, in.dtype_sr, in.gt, in.dtype_gt, B, H, W, Cfg::P, pad, st)) return e;
+    }
     if (int e = launch_plane_lists(in.mask, in.mask_channels, in.mask_stride, in.edges, in.n_edges_dev, max_edges, l.g,
                                    l.cap, ws, st, Cfg::SRP, 32 / Cfg::G)) return e;
     const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
@@ -280,9 +292,17 @@ inline int launch_plane_step_cfg(const StepInputs& in, int B, int H, int W, int 
     }
     float* q_sr = reinterpret_cast<float*>(ws + l.off_q[0]);
     float* q_gt = reinterpret_cast<float*>(ws + l.off_q[1]);
-    if (int e = launch_plane_forward_cfg<Cfg>(pad, 2, l.g, lists, l.cap, q_sr, q_gt,
-                                              reinterpret_cast<float*>(ws + l.off_eout[0]),
-                                              reinterpret_cast<float*>(ws + l.off_eout[1]), st)) return e;
+    float* eout_sr = reinterpret_cast<float*>(ws + l.off_eout[0]);
+    float* eout_gt = reinterpret_cast<float*>(ws + l.off_eout[1]);
+    if (in.gt_ready) {
+        // SR half first; the GT half as soon as the caller's copy of GT has landed
+        if (int e = launch_plane_forward_cfg<Cfg>(pad, 1, l.g, lists, l.cap, q_sr, nullptr, eout_sr, nullptr, st, 0, 2)) return e;
+        SSLB_CUDA(cudaStreamWaitEvent(st, in.gt_ready, 0));
+        if (int e = launch_pad(in.gt, in.dtype_gt, nullptr, in.dtype_gt, B, H, W, Cfg::P, pad_gt, st)) return e;
+        if (int e = launch_plane_forward_cfg<Cfg>(pad, 1, l.g, lists, l.cap, q_gt, nullptr, eout_gt, nullptr, st, 1, 2)) return e;
+    } else {
+        if (int e = launch_plane_forward_cfg<Cfg>(pad, 2, l.g, lists, l.cap, q_sr, q_gt, eout_sr, eout_gt, st)) return e;
+    }
     // rows -> loss terms and dL/dq (in place over q_sr) + per-class sums
     RowLossTParams rp{};
     rp.qs = q_sr; rp.qg = q_gt; rp.slot_pix = lists.slot_pix; rp.counts = lists.counts;
@@ -306,19 +326,14 @@ inline int launch_plane_step_cfg(const StepInputs& in, int B, int H, int W, int 
     return launch_plane_backward_cfg<Cfg>(pad, B, H, W, lists, l, ws, q_sr, nullptr, grad_sr, st);
 }
 
-// Rows backward behind the reference's operator API (similarity_map / compute_similarity): dL/dq rows in the
-// reference's order [n][L] -> dL/dimage, through the plane kernels.  Workspace = plane_step_layout(...).
+// dL/dq rows in the order of `edges` [n][L] -> padded-domain (grad == NULL, result in part 0 of gpart) or image-domain
+// gradient, through the plane kernels.  `pad` holds the padded image already; workspace = plane_step_layout(...).
 template <typename Cfg>
-inline int launch_plane_rows_backward_cfg(const void* img, int dtype, int B, int H, int W, const int32_t* edges,
-                                          const int32_t* counts, int max_edges, const float* gq_rows, float* grad,
-                                          void* workspace, size_t workspace_bytes, cudaStream_t st) {
+inline int launch_plane_rows_backward_padded_cfg(const float* pad, int B, int H, int W, const int32_t* edges,
+                                                 const int32_t* counts, int max_edges, const float* gq_rows,
+                                                 const PlaneStepLayout& l, char* ws, cudaStream_t st, float* grad = nullptr) {
     DeviceInfo di;
     if (int e = device_info(&di)) return e;
-    const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, 2 * di.sm_count, true);
-    SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
-    char* ws = static_cast<char*>(workspace);
-    float* pad = reinterpret_cast<float*>(ws + l.off_pad);
-    if (int e = launch_pad(img, dtype, nullptr, dtype, B, H, W, Cfg::P, pad, st)) return e;
     if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, max_edges, l.g, l.cap, ws, st, Cfg::SRP, 32 / Cfg::G)) return e;
     const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
     float* gqT = reinterpret_cast<float*>(ws + l.off_q[0]);
@@ -336,6 +351,22 @@ inline int launch_plane_rows_backward_cfg(const void* img, int dtype, int B, int
     }
     if (int e = check_launch("plane_rows_to_slots", 3)) return e;
     return launch_plane_backward_cfg<Cfg>(pad, B, H, W, lists, l, ws, gqT, gcls, grad, st);
+}
+
+// Rows backward behind the reference's operator API (similarity_map / compute_similarity): dL/dq rows in the
+// reference's order [n][L] -> dL/dimage, through the plane kernels.  Workspace = plane_step_layout(...).
+template <typename Cfg>
+inline int launch_plane_rows_backward_cfg(const void* img, int dtype, int B, int H, int W, const int32_t* edges,
+                                          const int32_t* counts, int max_edges, const float* gq_rows, float* grad,
+                                          void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const PlaneStepLayout l = plane_step_layout<Cfg>(B, H, W, max_edges, 2 * di.sm_count, true);
+    SSLB_REQUIRE(workspace_bytes >= l.total, "workspace too small (%zu < %zu)", workspace_bytes, l.total);
+    char* ws = static_cast<char*>(workspace);
+    float* pad = reinterpret_cast<float*>(ws + l.off_pad);
+    if (int e = launch_pad(img, dtype, nullptr, dtype, B, H, W, Cfg::P, pad, st)) return e;
+    return launch_plane_rows_backward_padded_cfg<Cfg>(pad, B, H, W, edges, counts, max_edges, gq_rows, l, ws, st, grad);
 }
 
 }  // namespace sslb

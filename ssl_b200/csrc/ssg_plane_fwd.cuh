@@ -24,6 +24,7 @@ namespace sslb {
 struct PlaneFwdParams {
     const float* pad;        // [2][B][3][Hp][pitch] reflect-padded fp32 images (pad.cuh); image 0 = SR, 1 = GT
     int Hp, pitch;
+    int img_first;           // padded image set of blockIdx.z == 0 (launches that cover one image of the two)
     float* qT[2];            // KS*KS x cap, panel layout (qt_index)
     const float* eout[2];    // [cap][NCLS*NCLS]
     PlaneLists lists;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
     const int Y0 = ty * Cfg::TYF - K + P, X0 = tx * Cfg::TXF + cx * 8 - p.g.xs - K + P;
     const int Wp = p.g.W + 2 * P;
     const long long plane = (long long)p.Hp * p.pitch;
-    const float* img = p.pad + ((long long)which * p.g.B + b) * 3 * plane;
+    const float* img = p.pad + ((long long)(p.img_first + which) * p.g.B + b) * 3 * plane;
     for (int i = threadIdx.x; i < ER * EC; i += blockDim.x) {
         const int ry = i / EC, rx = i - ry * EC;
         const int Y = Y0 + ry, X = X0 + rx;
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_fwd_kernel(const __
     // padded coordinates of the tile's first edge-pixel position: (P + ty*TYF, P + tx*TXF - xs); the window's
     // first column is a multiple of 4 (make_geom), as the copy engine requires
     issue_tile_load<Cfg>(tile, &tmap, &tile_bar, Cfg::P + tx * Cfg::TXF - p.g.xs - Cfg::K - Cfg::ICOL0,
-                         Cfg::P + ty * Cfg::TYF - Cfg::K - Cfg::P, (which * p.g.B + b) * 3);
+                         Cfg::P + ty * Cfg::TYF - Cfg::K - Cfg::P, ((p.img_first + which) * p.g.B + b) * 3);
     if (threadIdx.x <= Cfg::UNITS_X) ustart_s[threadIdx.x] = p.lists.unit_start[unit0 + threadIdx.x];
     const bool staged = slot1 - slot0 <= Cfg::RC_SMEM;
     if (staged)
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(256) plane_rows_to_reference_kernel(const floa
                                                                       const int32_t* slot_map, int L, float* rows) {
     const int mc = edge_count(n_edges_dev, max_edges);
     for (int n = blockIdx.x; n < mc; n += gridDim.x) {
-        const int slot = slot_map[edges[n]];
+        const int slot = edges[n] >= 0 ? slot_map[edges[n]] : -1;
         for (int d = threadIdx.x; d < L; d += blockDim.x)
             rows[(long long)n * L + d] = slot >= 0 && slot < cap ? qT[qt_index(d, slot, L)] : 0.f;
     }

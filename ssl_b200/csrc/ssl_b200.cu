@@ -84,12 +84,24 @@ int launch_point_backward(PointParams& p, int dtype, cudaStream_t st) {
 }  // namespace
 
 // ---- drop-in for similarity.h -------------------------------------------------------------
+// Dense masks (>= 2 % of the pixels) with a supported (k_s, k_w, C = 3) run on the plane kernels -- 3-4x faster at
+// the reference's mask densities and free of atomics (bitwise reproducible); everything else on the point kernels.
+namespace {
+bool ref_entry_uses_planes(int mc, int ks, int kw, int height, int width, int channel);
+int ref_forward_planes(const float* image, const int32_t* pos, float* out, int mc, int ks, int kw, int Hp, int Wp,
+                       cudaStream_t st);
+int ref_backward_planes(const float* image, const float* grads, const int32_t* pos, float* image_grads, int mc, int ks,
+                        int kw, int Hp, int Wp, cudaStream_t st);
+}  // namespace
+
 
 extern "C" int ssl_b200_compute_similarity(const float* image, const int32_t* pos, float* out, int mc, int psize,
                                            int ksize, int height, int width, int channel, void* stream) {
     SSLB_REQUIRE(image && out && (pos || mc == 0), "null pointer");
     SSLB_REQUIRE(mc >= 0, "negative mc");
     if (int e = check_sizes(psize, ksize, height, width, channel)) return e;
+    if (ref_entry_uses_planes(mc, psize, ksize, height, width, channel))
+        return ref_forward_planes(image, pos, out, mc, psize, ksize, height, width, (cudaStream_t)stream);
     PointParams p{};
     p.img[0] = image;
     p.rows[0] = out;
@@ -109,6 +121,9 @@ extern "C" int ssl_b200_compute_similarity_backward(const float* image, const fl
     SSLB_REQUIRE(image && image_grads && ((grads && pos) || mc == 0), "null pointer");
     SSLB_REQUIRE(mc >= 0, "negative mc");
     if (int e = check_sizes(psize, ksize, height, width, channel)) return e;
+    if (ref_entry_uses_planes(mc, psize, ksize, height, width, channel))
+        return ref_backward_planes(image, grads, pos, image_grads, mc, psize, ksize, height, width,
+                                   (cudaStream_t)stream);
     PointParams p{};
     p.img[0] = image;
     p.edges = EdgeRef{nullptr, pos};
@@ -277,6 +292,109 @@ PlaneFwdLayout plane_fwd_layout(int B, int H, int W, int max_edges) {
 bool plane_slots_fit(int B, int H, int W, int max_edges) {
     // (upper bound of the unit count over every plane geometry: TYF >= 48, TXF = 64, 8 units per tile row)
     return (long long)max_edges + 3ll * B * (H / 48 + 1) * (W / 64 + 2) * 8 < (1ll << 23);
+}
+
+}  // namespace
+
+namespace {
+
+// (row, col) in padded coordinates -> flat index of the unpadded image; positions outside the image interior
+// (which similaritywrapper.py:64-68 never produces) are dropped: their rows stay zero.
+__global__ void __launch_bounds__(256) pos_to_edges_kernel(const int32_t* pos, int mc, int P, int H, int W,
+                                                           int32_t* edges, int32_t* counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { counts[0] = mc; counts[1] = mc; }
+    if (i >= mc) return;
+    const int y = pos[2 * i] - P, x = pos[2 * i + 1] - P;
+    edges[i] = (y >= 0 && y < H && x >= 0 && x < W) ? y * W + x : -1;
+}
+
+// image_grads[c][Y][X] += G[c][Y][X] (the folded padded-domain gradient, HT x WT layout)
+__global__ void __launch_bounds__(256) add_padded_grad_kernel(const float* G, int HT, int WT, int Hp, int Wp,
+                                                              float* image_grads) {
+    const long long n = 3ll * Hp * Wp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % Wp), Y = (int)((i / Wp) % Hp), c = (int)(i / ((long long)Wp * Hp));
+        image_grads[i] += G[((long long)c * HT + Y) * WT + X];
+    }
+}
+
+bool ref_entry_uses_planes(int mc, int ks, int kw, int height, int width, int channel) {
+    const int P = ks / 2, H = height - 2 * P, W = width - 2 * P;
+    if (!plane_supported(ks, kw, channel) || H <= P || W <= P || mc <= 0) return false;
+    if (!plane_slots_fit(1, H, W, mc)) return false;
+    return (double)mc >= 0.02 * (double)H * W;
+}
+
+struct RefScratch {   // stream-ordered scratch of one drop-in call
+    char* base = nullptr;
+    cudaStream_t st;
+    ~RefScratch() { if (base) cudaFreeAsync(base, st); }
+};
+
+template <typename Cfg>
+int ref_forward_planes_cfg(const float* image, const int32_t* pos, float* out, int mc, int Hp, int Wp, cudaStream_t st) {
+    constexpr int P = Cfg::P;
+    const int H = Hp - 2 * P, W = Wp - 2 * P;
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const PlaneFwdLayout l = plane_fwd_layout<Cfg>(1, H, W, mc);
+    const size_t off_edges = l.total, off_counts = off_edges + align256((size_t)mc * sizeof(int32_t));
+    RefScratch sc; sc.st = st;
+    SSLB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sc.base), off_counts + 256, st));
+    char* ws = sc.base;
+    int32_t* edges = reinterpret_cast<int32_t*>(ws + off_edges);
+    int32_t* counts = reinterpret_cast<int32_t*>(ws + off_counts);
+    float* pad = reinterpret_cast<float*>(ws + l.off_pad);
+    const PadLayout pl = pad_layout(1, H, W, P);
+    pos_to_edges_kernel<<<(mc + 255) / 256, 256, 0, st>>>(pos, mc, P, H, W, edges, counts);
+    pad_copy_kernel<<<di.sm_count * 4, 256, 0, st>>>(image, 3, Hp, Wp, pl.pitch, pad);
+    if (int e = check_launch("ref_forward_prepare", 2)) return e;
+    if (int e = launch_plane_lists(nullptr, 1, 0, edges, counts, mc, l.g, l.cap, ws, st, Cfg::SRP, 32 / Cfg::G)) return e;
+    const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
+    float* q0 = reinterpret_cast<float*>(ws + l.off_q[0]);
+    if (int e = launch_plane_forward_cfg<Cfg>(pad, 1, l.g, lists, l.cap, q0, nullptr,
+                                              reinterpret_cast<float*>(ws + l.off_eout[0]), nullptr, st)) return e;
+    plane_rows_to_reference_kernel<<<min(mc, di.sm_count * 16), 256, 0, st>>>(q0, l.cap, edges, counts, mc, lists.slot_map,
+                                                                             Cfg::L, out);
+    return check_launch("plane_rows_to_reference");
+}
+
+template <typename Cfg>
+int ref_backward_planes_cfg(const float* image, const float* grads, const int32_t* pos, float* image_grads, int mc,
+                            int Hp, int Wp, cudaStream_t st) {
+    constexpr int P = Cfg::P;
+    const int H = Hp - 2 * P, W = Wp - 2 * P;
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const PlaneStepLayout l = plane_step_layout<Cfg>(1, H, W, mc, 2 * di.sm_count, true);
+    const size_t off_edges = l.total, off_counts = off_edges + align256((size_t)mc * sizeof(int32_t));
+    RefScratch sc; sc.st = st;
+    SSLB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sc.base), off_counts + 256, st));
+    char* ws = sc.base;
+    int32_t* edges = reinterpret_cast<int32_t*>(ws + off_edges);
+    int32_t* counts = reinterpret_cast<int32_t*>(ws + off_counts);
+    float* pad = reinterpret_cast<float*>(ws + l.off_pad);
+    pos_to_edges_kernel<<<(mc + 255) / 256, 256, 0, st>>>(pos, mc, P, H, W, edges, counts);
+    pad_copy_kernel<<<di.sm_count * 4, 256, 0, st>>>(image, 3, Hp, Wp, l.pad.pitch, pad);
+    if (int e = check_launch("ref_backward_prepare", 2)) return e;
+    // dL/dq rows -> slots -> padded-domain gradient (everything of the rows backward but the pad adjoint, which
+    // the caller's autograd applies: similaritywrapper.py:64)
+    if (int e = launch_plane_rows_backward_padded_cfg<Cfg>(pad, 1, H, W, edges, counts, mc, grads, l, ws, st)) return e;
+    add_padded_grad_kernel<<<di.sm_count * 4, 256, 0, st>>>(reinterpret_cast<const float*>(ws + l.off_gpart), l.HT, l.WT,
+                                                           Hp, Wp, image_grads);
+    return check_launch("add_padded_grad");
+}
+
+int ref_forward_planes(const float* image, const int32_t* pos, float* out, int mc, int ks, int kw, int Hp, int Wp,
+                       cudaStream_t st) {
+    SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg, { return ref_forward_planes_cfg<Cfg>(image, pos, out, mc, Hp, Wp, st); });
+}
+
+int ref_backward_planes(const float* image, const float* grads, const int32_t* pos, float* image_grads, int mc, int ks,
+                        int kw, int Hp, int Wp, cudaStream_t st) {
+    SSLB_DISPATCH_PLANE_CFG(ks, kw, Cfg,
+                            { return ref_backward_planes_cfg<Cfg>(image, grads, pos, image_grads, mc, Hp, Wp, st); });
 }
 
 }  // namespace
@@ -578,6 +696,8 @@ struct HostArena {
     char* base = nullptr;
     size_t bytes = 0;
     int32_t* counts_pinned = nullptr;
+    cudaStream_t copy_stream = nullptr;   // carries the GT upload while the SR half of the forward runs
+    cudaEvent_t counted = nullptr, sr_sent = nullptr, gt_ready = nullptr;
 };
 
 HostArena& arena() {
@@ -597,6 +717,12 @@ int arena_reserve(size_t bytes) {
         a.bytes = 0;
     }
     if (!a.counts_pinned) SSLB_CUDA(cudaMallocHost(&a.counts_pinned, 4 * sizeof(int32_t)));
+    if (!a.copy_stream) {
+        SSLB_CUDA(cudaStreamCreateWithFlags(&a.copy_stream, cudaStreamNonBlocking));
+        SSLB_CUDA(cudaEventCreateWithFlags(&a.counted, cudaEventDisableTiming));
+        SSLB_CUDA(cudaEventCreateWithFlags(&a.sr_sent, cudaEventDisableTiming));
+        SSLB_CUDA(cudaEventCreateWithFlags(&a.gt_ready, cudaEventDisableTiming));
+    }
     SSLB_CUDA(cudaMalloc(&a.base, bytes));
     a.bytes = bytes;
     a.dev = dev;
@@ -612,10 +738,22 @@ extern "C" int ssl_b200_release_host_arena(void) {
         SSLB_CUDA(cudaFree(a.base));
     }
     if (a.counts_pinned) SSLB_CUDA(cudaFreeHost(a.counts_pinned));
+    if (a.copy_stream) {
+        cudaEventDestroy(a.counted);
+        cudaEventDestroy(a.sr_sent);
+        cudaEventDestroy(a.gt_ready);
+        cudaStreamDestroy(a.copy_stream);
+    }
     a = HostArena{};
     return 0;
 }
 
+// Timeline of one call (st = the caller's stream, cs = the arena's copy stream):
+//   st: mask -> device, count edge pixels, count -> host | SR -> device | pad SR, lists, Eout + forward of SR |
+//       (wait for GT) pad GT, Eout + forward of GT, row loss, backward, mean, results -> host
+//   cs:                                                   (after SR)  GT -> device
+// The host reads the 4-byte count (it sizes the rows workspace) while SR is still on the wire, and the upload of
+// GT hides behind the SR half of the forward.
 extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_host, const float* mask_host,
                                        int mask_channels, int B, int C, int H, int W, int mask_stride, int ks, int kw,
                                        float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* loss_host,
@@ -625,58 +763,75 @@ extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_hos
     if (int e = check_sizes(ks, kw, H, W, C)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n_px = (size_t)B * H * W, img_bytes = align256(n_px * C * sizeof(float));
+    SSLB_REQUIRE(n_px < (1ull << 31), "batch too large for int32 pixel indices");
     const size_t mask_bytes = align256(n_px * mask_channels * sizeof(float));
-    const size_t edges_bytes = align256(n_px * sizeof(int32_t)), counts_bytes = align256((2 + B) * sizeof(int32_t));
-    const size_t el_ws = align256(ssl_b200_edge_list_workspace_bytes((int64_t)n_px));
-    const size_t small_bytes = 256;  // terms double[3] | loss float[3] | inv_n float
-    const size_t fixed = 3 * img_bytes + mask_bytes + edges_bytes + counts_bytes + el_ws + small_bytes;
-    // first pass with the arena we have (or the fixed part); rows need the edge count
+    const size_t small_bytes = 256;  // terms double[3] | loss float[3] | inv_n float | count int32
+    const size_t fixed = 3 * img_bytes + mask_bytes + small_bytes;
+    // first pass with the arena we have (or a guess of one edge pixel in eight); rows need the edge count
     HostArena& a = arena();
-    if (int e = arena_reserve(fixed + ssl_b200_loss_workspace_bytes(B, C, H, W, ks, kw, (int)(n_px / 8 + 1), 0))) return e;
+    if (int e = arena_reserve(fixed + ssl_b200_loss_step_workspace_bytes(B, C, H, W, ks, kw, (int)(n_px / 8 + 1), 0))) return e;
     auto carve = [&](char*& p, size_t b) { char* r = p; p += b; return r; };
     char* p = a.base;
     float* d_mask = (float*)carve(p, mask_bytes);
-    int32_t* d_edges = (int32_t*)carve(p, edges_bytes);
-    int32_t* d_counts = (int32_t*)carve(p, counts_bytes);
-    void* d_elws = carve(p, el_ws);
     char* d_small = carve(p, small_bytes);
+    float* d_sr = (float*)carve(p, img_bytes);
+    float* d_gt = (float*)carve(p, img_bytes);
+    float* d_grad = (float*)carve(p, img_bytes);
+    char* d_ws = p;
+    double* d_terms = (double*)d_small;
+    float* d_loss = (float*)(d_small + 64);
+    float* d_inv_n = (float*)(d_small + 128);
+    int32_t* d_count = (int32_t*)(d_small + 192);
     // mask first, so the edge count comes back while the images are still on the wire
     SSLB_CUDA(cudaMemcpyAsync(d_mask, mask_host, n_px * mask_channels * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (int e = ssl_b200_build_edge_list(d_mask, B, mask_channels, H, W, mask_stride, d_edges, (int)n_px, d_counts,
-                                         d_elws, el_ws, stream)) return e;
-    SSLB_CUDA(cudaMemcpyAsync(a.counts_pinned, d_counts, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    cudaEvent_t counted;
-    SSLB_CUDA(cudaEventCreateWithFlags(&counted, cudaEventDisableTiming));
-    SSLB_CUDA(cudaEventRecord(counted, st));
-    // images may land anywhere after the fixed head: if the arena must grow they are re-sent
-    auto place_images = [&](char* q, float*& d_sr, float*& d_gt, float*& d_grad, char*& d_ws) {
-        d_sr = (float*)carve(q, img_bytes);
-        d_gt = (float*)carve(q, img_bytes);
-        d_grad = (float*)carve(q, img_bytes);
-        d_ws = q;
-    };
-    float *d_sr, *d_gt, *d_grad;
-    char* d_ws;
-    place_images(p, d_sr, d_gt, d_grad, d_ws);
+    SSLB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int32_t), st));
+    {
+        DeviceInfo di;
+        if (int e = device_info(&di)) return e;
+        EdgeListParams ep{};
+        ep.mask = d_mask; ep.mask_channels = mask_channels; ep.H = H; ep.W = W; ep.stride = mask_stride;
+        ep.n_pixels = (long long)n_px;
+        StageTimer timer(kStageEdgeList, st);
+        mask_count_kernel<<<di.sm_count * 4, kElThreads, 0, st>>>(ep, d_count);
+        if (int e = check_launch("mask_count")) return e;
+    }
+    SSLB_CUDA(cudaMemcpyAsync(a.counts_pinned, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SSLB_CUDA(cudaEventRecord(a.counted, st));
     SSLB_CUDA(cudaMemcpyAsync(d_sr, sr_host, n_px * C * sizeof(float), cudaMemcpyHostToDevice, st));
-    SSLB_CUDA(cudaMemcpyAsync(d_gt, gt_host, n_px * C * sizeof(float), cudaMemcpyHostToDevice, st));
-    cudaError_t ce = cudaEventSynchronize(counted);
-    cudaEventDestroy(counted);
+    SSLB_CUDA(cudaEventRecord(a.sr_sent, st));
+    // GT follows SR on the copy stream (not beside it: SR is on the critical path)
+    SSLB_CUDA(cudaStreamWaitEvent(a.copy_stream, a.sr_sent, 0));
+    SSLB_CUDA(cudaMemcpyAsync(d_gt, gt_host, n_px * C * sizeof(float), cudaMemcpyHostToDevice, a.copy_stream));
+    SSLB_CUDA(cudaEventRecord(a.gt_ready, a.copy_stream));
+    cudaError_t ce = cudaEventSynchronize(a.counted);
     if (ce != cudaSuccess) return fail((int)ce, "edge count readback: %s", cudaGetErrorString(ce));
     const int n_rows = a.counts_pinned[0];
-    const size_t ws_bytes = ssl_b200_loss_workspace_bytes(B, C, H, W, ks, kw, n_rows, 0);
+    const size_t ws_bytes = ssl_b200_loss_step_workspace_bytes(B, C, H, W, ks, kw, n_rows, 0);
     if (fixed + ws_bytes > a.bytes) {
         // grow (rare: first call, or a denser mask than ever seen) and redo the uploads
+        SSLB_CUDA(cudaStreamSynchronize(a.copy_stream));
         if (int e = arena_reserve(fixed + ws_bytes + ws_bytes / 4)) return e;
         return ssl_b200_loss_step_host(sr_host, gt_host, mask_host, mask_channels, B, C, H, W, mask_stride, ks, kw,
                                        sigma, eps, rows_mode, w_l1, w_kl, loss_host, grad_host, n_rows_host, stream);
     }
-    double* d_terms = (double*)d_small;
-    float* d_loss = (float*)(d_small + 64);
-    float* d_inv_n = (float*)(d_small + 128);
-    if (int e = ssl_b200_loss_forward_backward(d_sr, d_gt, SSL_B200_F32, B, C, H, W, d_edges, d_counts, n_rows, ks, kw,
-                                               sigma, eps, rows_mode, w_l1, w_kl, grad_host ? d_grad : nullptr,
-                                               d_terms, d_ws, ws_bytes, SSL_B200_PATH_AUTO, stream)) return e;
+    {
+        StepInputs in{};
+        in.sr = d_sr; in.gt = d_gt; in.dtype_sr = SSL_B200_F32; in.dtype_gt = SSL_B200_F32;
+        in.mask = d_mask; in.mask_channels = mask_channels; in.mask_stride = mask_stride;
+        const bool plane = n_rows > 0 && use_plane_path(SSL_B200_PATH_AUTO, B, C, H, W, ks, kw, n_rows);
+        int rc;
+        if (plane) {
+            in.gt_ready = a.gt_ready;   // the step waits for GT itself, after the SR half of the forward
+            rc = loss_step_impl(in, nullptr, B, C, H, W, n_rows, ks, kw, sigma, eps, rows_mode, w_l1, w_kl,
+                                grad_host ? d_grad : nullptr, d_terms, d_ws, ws_bytes, SSL_B200_PATH_AUTO, st);
+        } else {
+            SSLB_CUDA(cudaStreamWaitEvent(st, a.gt_ready, 0));
+            rc = ssl_b200_loss_step(d_sr, SSL_B200_F32, d_gt, SSL_B200_F32, d_mask, mask_channels, mask_stride, B, C, H, W,
+                                    n_rows, ks, kw, sigma, eps, rows_mode, w_l1, w_kl, grad_host ? d_grad : nullptr,
+                                    d_terms, d_ws, ws_bytes, SSL_B200_PATH_AUTO, stream);
+        }
+        if (rc) return rc;
+    }
     finalize_loss_kernel<<<1, 1, 0, st>>>(d_terms, ks * ks, w_l1, w_kl, d_loss, d_inv_n);
     if (int e = check_launch("finalize_loss")) return e;
     SSLB_CUDA(cudaMemcpyAsync(loss_host, d_loss, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));

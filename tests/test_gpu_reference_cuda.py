@@ -144,3 +144,50 @@ def test_full_ssl_cuda_pipeline_equals_reference_cuda(dev, ref):
     assert s.shape == s_ref.shape
     err = (s.detach() - s_ref).abs() / s_ref.max(dim=-1, keepdim=True).values
     assert float(err.max()) <= 1e-5
+
+
+@pytest.mark.parametrize("density,family", [(0.2, "ssg_plane"), (0.004, "ssg_point")])
+def test_dropin_entries_pick_the_kernel_family_by_density(dev, ref, density, family):
+    """similarity.h drop-ins: dense masks run on the plane kernels (deterministic, no atomics), sparse ones on the
+    point kernels; both agree with the reference's CUDA op and with the fp64 oracle, forward and backward."""
+    from ssl_b200 import _lib, synth
+    ks, kw = 25, 9
+    sr, _, mask = synth.make_case(1, 96, 72, seed=17, density=density)
+    img, m = sr[0].numpy(), mask[0, 0].numpy()
+    img_pad, pos, pos_pad = _padded_inputs(dev, img, m, ks)
+    mc = len(pos)
+    c, hp, wp = img_pad.shape
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out_ref = torch.zeros(mc, ks, ks, device=dev)
+    torch.cuda.synchronize()
+    assert ref.ref_compute_similarity(_vp(img_pad), _vp(pos_pad), _vp(out_ref), mc, ks, kw, hp, wp, c) == 0
+    torch.cuda.synchronize()
+    g = torch.Generator().manual_seed(6)
+    grads = torch.randn(mc, ks * ks, generator=g).to(dev)
+    gi_ref = torch.zeros_like(img_pad)
+    assert ref.ref_compute_similarity_backward(_vp(img_pad), _vp(grads), _vp(pos_pad), _vp(gi_ref), mc, ks, kw, hp, wp,
+                                               c) == 0
+    torch.cuda.synchronize()
+    _lib.profile_enable(True)
+    out = torch.full((mc, ks, ks), float("nan"), device=dev)
+    _lib.call("ssl_b200_compute_similarity", _vp(img_pad), _vp(pos_pad), _vp(out), mc, ks, kw, hp, wp, c, st)
+    gi = torch.full_like(img_pad, 0.25)                       # contributions are ADDED into the caller's buffer
+    _lib.call("ssl_b200_compute_similarity_backward", _vp(img_pad), _vp(grads), _vp(pos_pad), _vp(gi), mc, ks, kw, hp,
+              wp, c, st)
+    torch.cuda.synchronize()
+    stages = _lib.profile_read()
+    _lib.profile_enable(False)
+    assert family + "_fwd" in stages and family + "_bwd" in stages, stages
+    np.testing.assert_allclose(out.cpu().numpy(), out_ref.cpu().numpy(), rtol=2e-6, atol=1e-7)
+    P = ks // 2
+    g64 = oracle.raw_distance_backward(img_pad.cpu().numpy().astype(np.float64), pos + P,
+                                       grads.cpu().numpy().astype(np.float64), ks, kw)
+    gmax = np.abs(g64).max()
+    assert np.abs(gi.cpu().numpy() - 0.25 - g64).max() <= 1e-5 * gmax
+    assert np.abs(gi.cpu().numpy() - 0.25 - gi_ref.cpu().numpy()).max() <= 1e-5 * gmax
+    if family == "ssg_plane":   # no atomics on this path: a second call gives the same bits
+        gi2 = torch.full_like(img_pad, 0.25)
+        _lib.call("ssl_b200_compute_similarity_backward", _vp(img_pad), _vp(grads), _vp(pos_pad), _vp(gi2), mc, ks, kw,
+                  hp, wp, c, st)
+        torch.cuda.synchronize()
+        assert torch.equal(gi, gi2)
