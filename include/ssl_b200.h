@@ -21,6 +21,8 @@
  *   ssl_b200_loss_step_host                same block in 7 other *ssl_model.py, train_BSGRAN/models/model_ssl.py:285-334,
  *                                          Diffusion-Based-SR/ldm/models/diffusion/ddpmssl.py:438-513)
  *   ssl_b200_laplacian_mask                GAN-Based-SR/scripts/data_preparation/generate_mask.py:22-31
+ *   ssl_b200_crop                          GAN-Based-SR/basicsr/data/transforms.py:93-149 (paired_random_crop_img_mask)
+ *   ssl_b200_pool_exchange                 GAN-Based-SR/basicsr/models/realesrganssl_model.py:326-367 (_dequeue_and_enqueue)
  */
 #ifndef SSL_B200_H_
 #define SSL_B200_H_
@@ -200,6 +202,21 @@ int ssl_b200_loss_step_host(const float* sr_host, const float* gt_host, const fl
                             int64_t* n_rows_host, void* stream);
 /* Frees the cached arena of the current device. */
 int ssl_b200_release_host_arena(void);
+
+/* ---- the step upstream of the loss: crop + training-pair pool that carry the mask ------- */
+
+/* dst[p][y][x] = src[p][top + y][left + x] for `planes` planes of 4-byte elements (any fp32 / int32 tensor viewed
+ * as [planes, H, W]): the tensor branch of paired_random_crop_img_mask (GAN-Based-SR/basicsr/data/transforms.py:
+ * 93-149), which crops LQ, GT and the edge mask with one (top, left) draw. */
+int ssl_b200_crop(const void* src, void* dst, int planes, int H, int W, int top, int left, int h, int w, void* stream);
+
+/* One tensor of the training-pair pool (GAN-Based-SR/basicsr/models/realesrganssl_model.py:326-367): for i < b
+ *     out[i] = queue[slots[i]]   (out == NULL: enqueue only),   queue[slots[i]] = in[i]
+ * on samples of `sample_elems` 4-byte elements.  bcast_channels > 1: `in` holds ONE channel per sample that is
+ * written to all bcast_channels channels of the queue sample -- the reference allocates the mask queue with the
+ * GT's channel count and assigns the 1-channel mask into it (:339-341,357).  slots: int32 [b] on the device. */
+int ssl_b200_pool_exchange(void* queue, const void* in, void* out, const int32_t* slots, int b, int64_t sample_elems,
+                           int bcast_channels, void* stream);
 
 /* Optional per-stage timing of the entry points above.  While enabled, every stage (edge list,
  * plane lists, forward, row loss, backward, ...) is bracketed by CUDA events recorded on the stream

@@ -6,6 +6,7 @@ Public surface:
     compute_similarity               drop-in for basicsr.losses.similarity.similaritywrapper.compute_similarity
     build_edge_list, ssg_rows, laplacian_mask   the pieces
     ssl_step_host                    the same step on host buffers (H2D + step + D2H in one C-ABI call)
+    paired_random_crop_img_mask, TrainingPairPool   the crop and the pair pool that carry the mask upstream of the loss
 Importing the package does not need a GPU; calling any operator without CUDA tensors or without
 the built library raises (there is no fallback path).
 """
@@ -13,7 +14,8 @@ from .compat import similarity_map
 from .functional import (EdgeList, build_edge_list, compute_similarity, laplacian_mask, ssg_rows,
                          ssl_step_host)
 from .loss import SelfSimilarityLoss, ssl
+from .pool import TrainingPairPool, paired_random_crop_img_mask
 
 __all__ = ["SelfSimilarityLoss", "ssl", "similarity_map", "compute_similarity", "build_edge_list", "ssg_rows",
-           "laplacian_mask", "EdgeList", "ssl_step_host"]
+           "laplacian_mask", "EdgeList", "ssl_step_host", "TrainingPairPool", "paired_random_crop_img_mask"]
 __version__ = "0.1.0"

@@ -66,6 +66,9 @@ SIGNATURES = {
                                          _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_float, _c_float,
                                          _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ssl_b200_release_host_arena": (_c_int, []),
+    "ssl_b200_crop": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "ssl_b200_pool_exchange": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.c_int64, _c_int,
+                                        _c_void_p]),
     "ssl_b200_profile_enable": (_c_int, [_c_int]),
     "ssl_b200_profile_num_stages": (_c_int, []),
     "ssl_b200_profile_stage_name": (ctypes.c_char_p, [_c_int]),

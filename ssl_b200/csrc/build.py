@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libssl_b200.so")
 SOURCES = ["ssl_b200.cu"]
 HEADERS = ["common.cuh", "edge_list.cuh", "row_ops.cuh", "ssg_point.cuh", "plane_geom.cuh", "plane_host.cuh",
-           "ssg_plane_fwd.cuh", "ssg_plane_bwd.cuh", "row_loss_t.cuh", "pad.cuh", "tma.cuh",
+           "ssg_plane_fwd.cuh", "ssg_plane_bwd.cuh", "row_loss_t.cuh", "pad.cuh", "tma.cuh", "pool_ops.cuh",
            os.path.join(ROOT, "include", "ssl_b200.h")]
 
 

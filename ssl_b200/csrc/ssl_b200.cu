@@ -7,6 +7,7 @@
 #include "row_ops.cuh"
 #include "ssg_point.cuh"
 #include "plane_host.cuh"
+#include "pool_ops.cuh"
 
 using namespace sslb;
 
@@ -846,6 +847,37 @@ extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_hos
     SSLB_CUDA(cudaStreamSynchronize(st));
     if (n_rows_host) *n_rows_host = n_rows;
     return 0;
+}
+
+// ---- crop + training-pair pool -------------------------------------------------
+
+extern "C" int ssl_b200_crop(const void* src, void* dst, int planes, int H, int W, int top, int left, int h, int w,
+                             void* stream) {
+    SSLB_REQUIRE(src && dst, "null pointer");
+    SSLB_REQUIRE(planes >= 1 && h >= 1 && w >= 1 && top >= 0 && left >= 0 && top + h <= H && left + w <= W,
+                 "crop [%d:%d, %d:%d] does not fit %dx%d", top, top + h, left, left + w, H, W);
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const long long n = (long long)planes * h * w;
+    const int blocks = (int)min((long long)di.sm_count * 8, (n + 255) / 256);
+    crop_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst),
+                                                          planes, H, W, top, left, h, w);
+    return check_launch("crop");
+}
+
+extern "C" int ssl_b200_pool_exchange(void* queue, const void* in, void* out, const int32_t* slots, int b,
+                                      int64_t sample_elems, int bcast_channels, void* stream) {
+    SSLB_REQUIRE(queue && in && slots, "null pointer");
+    SSLB_REQUIRE(b >= 1 && sample_elems >= 1, "bad sizes");
+    SSLB_REQUIRE(bcast_channels <= 1 || sample_elems % bcast_channels == 0, "sample size is not a multiple of the channels");
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const long long n = (long long)b * sample_elems;
+    const int blocks = (int)min((long long)di.sm_count * 8, (n + 255) / 256);
+    pool_exchange_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<uint32_t*>(queue), static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), slots, b,
+        (long long)sample_elems, bcast_channels, bcast_channels > 1 ? (long long)sample_elems / bcast_channels : 0);
+    return check_launch("pool_exchange");
 }
 
 extern "C" int ssl_b200_profile_enable(int on) {
