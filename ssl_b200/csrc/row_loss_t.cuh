@@ -165,43 +165,60 @@ __global__ void __launch_bounds__(kRowTThreads, 2) row_loss_t_kernel(RowLossTPar
             //      the row classes.  Rows of 16 slots are contiguous in wtab: written as one coalesced block.
             if (p.wtab) {
                 constexpr int U = P - K;
-                for (int c = ph; c < NC * NC; c += NPH) {
-                    const int ca = c / NC, cb = c % NC;
+                // (a) the 4K classes of one clipped dy (or dx) against all unclipped dx (dy) are sums of 2U+1 offsets in
+                //     a row (column) of the offset grid: one per phase; the 4K^2 corner classes are single offsets
+                if (ph < 4 * K) {
+                    const int q = ph % (2 * K);                    // which clipped value
+                    const int cc = q < K ? q : q + 1;              // its class (the unclipped class K is skipped)
+                    const int t = cc < K ? cc - P : U + (cc - K);  // the clipped dy (rows) or dx (columns)
+                    const bool row_class = ph < 2 * K;
+                    const int d0 = row_class ? (t + P) * KS + (P - U) : (P - U) * KS + t + P;
+                    const int stride = row_class ? NS : KS * NS;
+                    const float* src = gqbuf + d0 * NS + s;
                     float acc = 0.f;
-                    if (ca != K || cb != K) {
-                        const int dy0 = ca < K ? ca - P : (ca > K ? U + (ca - K) : -U);
-                        const int dy1 = ca == K ? U : dy0;
-                        const int dx0 = cb < K ? cb - P : (cb > K ? U + (cb - K) : -U);
-                        const int dx1 = cb == K ? U : dx0;
-                        for (int dy = dy0; dy <= dy1; ++dy) {
-                            const float* row = gqbuf + ((dy + P) * KS + dx0 + P) * NS + s;
-                            for (int dx = dx0; dx <= dx1; ++dx, row += NS) acc += *row;
-                        }
+#pragma unroll
+                    for (int i = 0; i < 2 * U + 1; ++i) acc += src[i * stride];
+                    sG[row_class ? cc * NC + K : K * NC + cc][s] = acc;
+                } else {
+                    for (int j = ph - 4 * K; j < 4 * K * K; j += NPH - 4 * K) {
+                        const int qa = j / (2 * K), qb = j % (2 * K);
+                        const int ca = qa < K ? qa : qa + 1, cb = qb < K ? qb : qb + 1;
+                        const int dy = ca < K ? ca - P : U + (ca - K), dx = cb < K ? cb - P : U + (cb - K);
+                        sG[ca * NC + cb][s] = gqbuf[((dy + P) * KS + dx + P) * NS + s];
                     }
-                    sG[c][s] = acc;
                 }
                 __syncthreads();
-                for (int i = ph; i < NC * KW; i += NPH) {          // sT[ca][b]: column b of the window out of class cb
-                    const int ca = i / KW, b = i % KW - K;
-                    float acc = 0.f;
+                // (b) window column b is out of area for the classes cb < -b (b < 0) or cb > 2K - b (b > 0): running
+                //     sums over cb from either end; sR = the whole row class
+                if (ph < NC) {
+                    const int ca = ph;
+                    float g9[NC];
 #pragma unroll
-                    for (int cb = 0; cb < NC; ++cb)
-                        if (b < class_lo(cb, K) || b > class_hi(cb, K)) acc += sG[ca * NC + cb][s];
-                    sT[i][s] = acc;
-                }
-                if (ph < NC) {                                      // sR[ca]: everything of row class ca
-                    float acc = 0.f;
+                    for (int cb = 0; cb < NC; ++cb) g9[cb] = (ca == K && cb == K) ? 0.f : sG[ca * NC + cb][s];
+                    float lo = 0.f, hi = 0.f, all = 0.f;
+                    sT[ca * KW + K][s] = 0.f;
 #pragma unroll
-                    for (int cb = 0; cb < NC; ++cb) acc += sG[ph * NC + cb][s];
-                    sR[ph][s] = acc;
+                    for (int m = 1; m <= K; ++m) {
+                        lo += g9[m - 1];
+                        hi += g9[NC - m];
+                        sT[ca * KW + K - m][s] = lo;      // b = -m
+                        sT[ca * KW + K + m][s] = hi;      // b = +m
+                    }
+#pragma unroll
+                    for (int cb = 0; cb < NC; ++cb) all += g9[cb];
+                    sR[ca][s] = all;
                 }
                 __syncthreads();
+                // (c) window row a is out of area for the classes ca < -a or ca > 2K - a: those count in full (sR),
+                //     the others with their out-of-area columns (sT)
                 for (int i = ph; i < KW * KW; i += NPH) {
                     const int a = i / KW - K, b = i % KW;
                     float acc = 0.f;
 #pragma unroll
-                    for (int ca = 0; ca < NC; ++ca)
-                        acc += (a < class_lo(ca, K) || a > class_hi(ca, K)) ? sR[ca][s] : sT[ca * KW + b][s];
+                    for (int ca = 0; ca < NC; ++ca) {
+                        const bool out = (a < 0 && ca < -a) || (a > 0 && ca > 2 * K - a);
+                        acc += out ? sR[ca][s] : sT[ca * KW + b][s];
+                    }
                     sW[s * (KW * KW) + i] = acc;
                 }
                 __syncthreads();
