@@ -254,11 +254,15 @@ __device__ __forceinline__ void sweep_chunk_fwd(const float* tile, float* splane
         constexpr int shift = Cfg::K - rng_hi(GC::DX0 + j, Cfg::P, Cfg::K);
         float s[8];
         box_last<len>(d[j], carry[j], s);
+#ifdef SSLB_EXPERIMENT_NORING     // timing experiment only: no ring stores (one conditional store keeps the math alive)
+        if (s[0] + s[7] == 123.456f) spa[j * Cfg::SPS] = s[3];
+#else
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (i + shift < 8) spa[j * Cfg::SPS + i + shift] = s[i];
             else spb[j * Cfg::SPS + i + shift - 8] = s[i];
         }
+#endif
     });
 }
 
@@ -315,7 +319,11 @@ __device__ __forceinline__ void run_group_fwd(const PlaneFwdParams& p, const flo
             }
             sweep_chunk_fwd<Cfg, GI>(tile, splanes, r, dy, wp, k, carry);
             worker_sync<Cfg::ROWS>(wp);
+#ifdef SSLB_EXPERIMENT_NOGATHER   // timing experiment only: the sweep without the gather
+            if (g_ok && carry[0].s8 == 123.456f) {
+#else
             if (g_ok) {
+#endif
                 for (int gs = gs_first; gs < s1; gs += 4 * NGRP) {
                     const int4 rc4 = *reinterpret_cast<const int4*>(slot_rc + (gs - slot0));
                     const int rcs[4] = {rc4.x, rc4.y, rc4.z, rc4.w};
