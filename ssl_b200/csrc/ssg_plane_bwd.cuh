@@ -23,6 +23,46 @@
 
 namespace sslb {
 
+// ---- tensor memory (TMEM) as the accumulator store ---------------------------------------------
+// Blackwell's 256 KB of tensor memory per SM (128 lanes x 512 32-bit columns) is reachable from ordinary warps
+// with tcgen05.ld / tcgen05.st, on a datapath of its own: nothing of it goes through the shared-memory pipe that
+// bounds this kernel.  A warp reaches the 32 lanes of its own quarter (warp id mod 4) -- with lane = image row,
+// which is exactly how a worker holds its partial sums -- so the CTA keeps FOUR partial accumulator tiles, one per
+// quarter, each shared by the three workers whose warp id falls into it; they are added up (in quarter order)
+// once, at the end.  `#define SSLB_BWD_TMEM 0` builds the shared-memory accumulator of round 1 instead.
+#ifndef SSLB_BWD_TMEM
+#define SSLB_BWD_TMEM 1
+#endif
+
+__device__ __forceinline__ void tmem_alloc_512(uint32_t* smem_slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// 8 consecutive columns of the calling thread's lane (lane = quarter base + lane id)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 #ifdef SSLB_EXPERIMENT_NOGQ   // timing experiment only: how much of the kernel is the dL/dq gather?
 #define SSLB_GQ(gq, packed) (1e-9f * (float)((packed) & 1023))
 #else
@@ -337,7 +377,8 @@ __device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* 
 // lanes, and lane 0 releases the next ticket after the warp's updates.
 template <typename Cfg, int GI>
 __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const float* tile, float* ubuf, float* accT,
-                                              const int32_t* cols, const uint8_t* cum, const int32_t* ent, int* turn) {
+                                              const int32_t* cols, const uint8_t* cum, const int32_t* ent, int* turn,
+                                              uint32_t tmem_base) {
     using GC = GroupConsts<Cfg, GI>;
     using BC = PlaneBwdCfg<Cfg>;
     constexpr int P = Cfg::P, GJ = GC::GJ, NWP = Cfg::NWP;
@@ -365,7 +406,13 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
             k_end = wp + 2;
             if (wp >= BC::NCHB - 1) break;
         }
+#if SSLB_BWD_TMEM
+        // additions into (quarter, output chunk) are ordered among the workers of the quarter: (item, worker / 4)
+        constexpr int WQ = (NWP + 3) / 4;
+        const int ticket = item * WQ + (item < BC::FULL_ROUNDS || !BC::SPLIT_LAST ? wp / 4 : 0);
+#else
         const int ticket = item * NWP + (item < BC::FULL_ROUNDS || !BC::SPLIT_LAST ? wp : 0);
+#endif
 #pragma unroll
         for (int j = 0; j < GJ; ++j) box_carry_reset(carry[j]);
         constexpr int NB = BC::NB;
@@ -386,12 +433,31 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
             sweep_chunk_bwd<Cfg, GI>(tile, uworker, r, dy, k, k == k_begin, carry, acc);
             // 3. add into the accumulator tile (output chunk k-1) when it is this worker's turn
             if (k > k_begin) {
+#if SSLB_BWD_TMEM
+                cuda::atomic_ref<int, cuda::thread_scope_block> tk(turn[(wp & 3) * BC::NCHB + k - 1]);
+#else
                 cuda::atomic_ref<int, cuda::thread_scope_block> tk(turn[k - 1]);
+#endif
 #ifndef SSLB_EXPERIMENT_NOTICKET
                 if (r == 0)
                     while (tk.load(cuda::memory_order_acquire) != ticket) __nanosleep(32);
 #endif
                 __syncwarp();
+#if SSLB_BWD_TMEM
+                tmem_fence_after_sync();
+                // lane = row: the thread's 8 columns of every channel are 8 consecutive TMEM columns of its lane
+                const uint32_t ta = tmem_base + ((uint32_t)((wp & 3) * 32) << 16) + 8 * (k - 1);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float v[8];
+                    tmem_ld8(ta + c * BC::TXB, v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += acc[c][i];
+                    tmem_st8(ta + c * BC::TXB, v);
+                }
+                tmem_wait_st();
+                tmem_fence_before_sync();
+#else
 #ifdef SSLB_EXPERIMENT_NOACC
                 if (acc[0][0] == 123.456f)
 #endif
@@ -403,6 +469,7 @@ __device__ __forceinline__ void run_group_bwd(const PlaneBwdParams& p, const flo
                     v1.x += acc[c][4]; v1.y += acc[c][5]; v1.z += acc[c][6]; v1.w += acc[c][7];
                     dst[0] = v0; dst[1] = v1;
                 }
+#endif
                 __syncwarp();
                 if (r == 0) tk.store(ticket + 1, cuda::memory_order_release);
             }
@@ -421,9 +488,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(const __
     int32_t* ent_s = reinterpret_cast<int32_t*>(accT + 3 * Cfg::ROWS * BC::ACC_PITCH);
     uint8_t* cum_s = reinterpret_cast<uint8_t*>(ent_s + BC::LIST_SMEM);
     __shared__ int32_t cols_s[BC::RCOLS + 1];
-    __shared__ int turn_s[BC::NCHB];
+    __shared__ int turn_s[4 * BC::NCHB];
     __shared__ __align__(8) uint64_t tile_bar;
-    if (threadIdx.x < BC::NCHB) turn_s[threadIdx.x] = 0;
+    __shared__ uint32_t tmem_slot;
+    if (threadIdx.x < 4 * BC::NCHB) turn_s[threadIdx.x] = 0;
     const int t = blockIdx.x;
     const int txb = t % p.ntxb, tyb = (t / p.ntxb) % p.ntyb, b = t / (p.ntxb * p.ntyb);
     const int32_t* cols_g = p.tile_cols + (long long)t * (BC::RCOLS + 1);
@@ -438,6 +506,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(const __
         return;
     }
     issue_tile_load<Cfg>(tile, &tmap, &tile_bar, Xb0 - 8 - Cfg::ICOL0, Yb0 - Cfg::P, b * 3);
+#if SSLB_BWD_TMEM
+    static_assert(3 * BC::TXB <= 512 && Cfg::ROWS == 32, "one TMEM lane per image row, 3 * TXB columns per quarter");
+    if (threadIdx.x < 32) tmem_alloc_512(&tmem_slot);   // warp 0 (the whole warp) allocates all 512 columns
+    tmem_fence_before_sync();
+#endif
     for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::ACC_PITCH; i += blockDim.x) accT[i] = 0.f;
     for (int i = threadIdx.x; i <= BC::RCOLS; i += blockDim.x) cols_s[i] = cols_g[i];
     {
@@ -451,18 +524,57 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(const __
         for (int i = threadIdx.x; i < n_ent; i += blockDim.x) ent_s[i] = ent_g[i];
     const int32_t* ent = staged ? ent_s : ent_g;
     __syncthreads();
+    uint32_t tmem_base = 0;
+#if SSLB_BWD_TMEM
+    tmem_fence_after_sync();
+    tmem_base = tmem_slot;
+    if (threadIdx.x < 128) {   // warps 0..3 clear their quarter's partial accumulator
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint32_t ta = tmem_base + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+        for (int c = 0; c < 3 * BC::TXB; c += 8) tmem_st8(ta + c, z);
+        tmem_wait_st();
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+#endif
     mbar_wait(&tile_bar, 0);
     switch (blockIdx.y) {
-        case 0: run_group_bwd<Cfg, 0>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
-        case 1: if constexpr (Cfg::NDXG > 1) run_group_bwd<Cfg, 1>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
-        case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
-        case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
-        case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
-        case 5: if constexpr (Cfg::NDXG > 5) run_group_bwd<Cfg, 5>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
-        case 6: if constexpr (Cfg::NDXG > 6) run_group_bwd<Cfg, 6>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s); break;
+        case 0: run_group_bwd<Cfg, 0>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+        case 1: if constexpr (Cfg::NDXG > 1) run_group_bwd<Cfg, 1>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+        case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+        case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+        case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+        case 5: if constexpr (Cfg::NDXG > 5) run_group_bwd<Cfg, 5>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+        case 6: if constexpr (Cfg::NDXG > 6) run_group_bwd<Cfg, 6>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
         default: break;
     }
+#if SSLB_BWD_TMEM
+    // the four quarter accumulators are added into the (zeroed) shared tile in quarter order, then TMEM is released
+    tmem_fence_before_sync();
     __syncthreads();
+    tmem_fence_after_sync();
+    for (int q = 0; q < 4; ++q) {
+        if ((threadIdx.x >> 5) == q) {
+            const int r = threadIdx.x & 31;
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16);
+            for (int c = 0; c < 3; ++c)
+                for (int x = 0; x < BC::TXB; x += 8) {
+                    float v[8];
+                    tmem_ld8(ta + c * BC::TXB + x, v);
+                    float* dst = accT + (c * Cfg::ROWS + r) * BC::ACC_PITCH + x;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] += v[i];
+                }
+        }
+        __syncthreads();
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc_512(tmem_base);
+#else
+    __syncthreads();
+#endif
     // the factor 2 of d(t^2) is applied here, once
     for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::TXB; i += blockDim.x) {
         const int xo = i % BC::TXB, rr = (i / BC::TXB) % Cfg::ROWS, c = i / (BC::TXB * Cfg::ROWS);
