@@ -147,7 +147,7 @@ inline int launch_plane_forward_cfg(const float* pad, int n_img, const PlaneGeom
     if (int e = make_plane_map(&tmap, pad, n_pad_sets * g.B * 3, pl.Hp, pl.Wp, pl.pitch, Cfg::IPITCH, Cfg::IROWS, 3)) return e;
     {
         StageTimer timer(kStageEout, st);
-        plane_eout_kernel<Cfg><<<dim3(g.n_units, n_img), 128, 0, st>>>(p);
+        plane_eout_kernel<Cfg><<<dim3(g.n_units, n_img), kEoutThreads, 0, st>>>(p);
     }
     auto k = ssg_plane_fwd_kernel<Cfg>;
     SSLB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

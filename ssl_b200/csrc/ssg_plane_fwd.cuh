@@ -36,15 +36,20 @@ struct PlaneFwdParams {
 // eout[slot][ca*NCLS+cb] = sum over window offsets (a,b) outside A(ca) x A(cb) of sum_c I(p+(a,b))^2.
 // One block per unit (8 columns x TYF rows of edge-pixel positions): the squared norms E2 = sum_c I^2 of the
 // unit's (TYF + 2K) x (8 + 2K) neighbourhood are formed once in shared memory and shared by all of its slots
-// (every E2 value serves up to (2K+1)^2 of them); then one warp per slot.  The complement of a clip range is
-// a prefix or a suffix of the window, so every entry is a sum of at most two running sums (all terms
-// non-negative, no subtraction).
+// (every E2 value serves up to (2K+1)^2 of them); then ONE THREAD per slot builds the whole table in registers.
+// The complement of a clip range is a prefix or a suffix of the window in each direction, so with running sums
+// along the window rows (pre / suf / full) and then along the window columns every entry costs one or two
+// additions; all terms are non-negative and nothing is subtracted.  Tables leave through shared memory so that the
+// global stores are contiguous.
+constexpr int kEoutThreads = 64;
+
 template <typename Cfg>
-__global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
-    constexpr int K = Cfg::K, KW = Cfg::KW, NC = Cfg::NCLS, NW = KW * KW, P = Cfg::P;
+__global__ void __launch_bounds__(kEoutThreads) plane_eout_kernel(PlaneFwdParams p) {
+    constexpr int K = Cfg::K, KW = Cfg::KW, NC = Cfg::NCLS, P = Cfg::P;
     constexpr int ER = Cfg::ROWS, EC = 8 + 2 * K, EP = EC + 1;   // region rows, columns, pitch
+    constexpr int OP = NC * NC + 1;                              // odd pitch of the staged tables
     __shared__ float sE2[ER * EP];
-    __shared__ float sE[4][NW], sPre[4][KW][K + 1], sSuf[4][KW][K + 1], sFull[4][KW];
+    __shared__ float sOut[kEoutThreads * OP];
     const int u = blockIdx.x, which = blockIdx.y;
     const int slot0 = p.lists.unit_start[u], slot1 = min(p.lists.unit_start[u + 1], p.cap);
     if (slot0 >= slot1) return;
@@ -70,58 +75,87 @@ __global__ void __launch_bounds__(128) plane_eout_kernel(PlaneFwdParams p) {
         sE2[ry * EP + rx] = e;
     }
     __syncthreads();
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int slot = slot0 + w; slot < slot1; slot += 4) {
-        const int rc = p.lists.slot_rc[slot];
-        float* out = const_cast<float*>(which ? p.eout[1] : p.eout[0]) + (long long)slot * (NC * NC);
-        if (rc < 0) {
-            for (int i = lane; i < NC * NC; i += 32) out[i] = 0.f;
-            continue;
-        }
-        const int re = rc >> 8, lx = (rc & 255) & 7;   // row lane (tile row + K), column inside the unit
-        for (int i = lane; i < NW; i += 32) {
-            const int a = i / KW, bb = i % KW;         // window offset (a - K, bb - K)
-            sE[w][i] = sE2[(re - K + a) * EP + lx + bb];
-        }
-        __syncwarp();
-        if (lane < KW) {  // one window row per lane: running sums from the left and from the right
-            const float* row = &sE[w][lane * KW];
-            float pre = 0.f, suf = 0.f, full = 0.f;
-            sPre[w][lane][0] = 0.f;
-            sSuf[w][lane][0] = 0.f;
-#pragma unroll
-            for (int m = 0; m < K; ++m) {
-                pre += row[m];
-                suf += row[KW - 1 - m];
-                sPre[w][lane][m + 1] = pre;
-                sSuf[w][lane][m + 1] = suf;
-            }
-#pragma unroll
-            for (int m = 0; m < KW; ++m) full += row[m];
-            sFull[w][lane] = full;
-        }
-        __syncwarp();
-        if (lane < NC) {  // one column class per lane
-            const int cb = lane;
-            // r[a] = sum over the columns of row a that are out of area for class cb
-            float r[KW], f[KW];
+    float* eout = const_cast<float*>(which ? p.eout[1] : p.eout[0]);
+    for (int base = slot0; base < slot1; base += kEoutThreads) {
+        const int slot = base + threadIdx.x;
+        const int rc = slot < slot1 ? p.lists.slot_rc[slot] : -1;
+        float* mine = sOut + threadIdx.x * OP;
+        if (rc >= 0) {
+            const int re = rc >> 8, lx = (rc & 255) & 7;   // row lane (tile row + K), column inside the unit
+            const float* win = sE2 + (re - K) * EP + lx;   // window (a, b) at win[a * EP + b], a, b in [0, KW)
+            // per window row: sum of its first m / last m columns (m = 1..K) and of all of them
+            float pre[KW][K + 1], suf[KW][K + 1], full[KW];
 #pragma unroll
             for (int a = 0; a < KW; ++a) {
-                r[a] = cb < K ? sPre[w][a][K - cb] : (cb > K ? sSuf[w][a][cb - K] : 0.f);
-                f[a] = sFull[w][a];
-            }
-            // row classes: rows out of area are the first (ca < K) or the last (ca > K) few; they count in full,
-            // the others only with their out-of-area columns
+                float e[KW];
 #pragma unroll
-            for (int ca = 0; ca < NC; ++ca) {
-                const int n_top = ca < K ? K - ca : 0, n_bot = ca > K ? ca - K : 0;
-                float s = 0.f;
+                for (int bb = 0; bb < KW; ++bb) e[bb] = win[a * EP + bb];
+                pre[a][0] = 0.f;
+                suf[a][0] = 0.f;
 #pragma unroll
-                for (int a = 0; a < KW; ++a) s += (a < n_top || a >= KW - n_bot) ? f[a] : r[a];
-                out[ca * NC + cb] = s;
+                for (int m = 1; m <= K; ++m) {
+                    pre[a][m] = pre[a][m - 1] + e[m - 1];
+                    suf[a][m] = suf[a][m - 1] + e[KW - m];
+                }
+                float mid = e[K];
+#pragma unroll
+                for (int m = 1; m < K; ++m) mid += e[K - m] + e[K + m];          // e[1..KW-2]
+                full[a] = (pre[a][1] + mid) + suf[a][1];                        // + e[0] + e[KW-1]
             }
+            // rows out of area count in full: running sums of `full` from the top and from the bottom
+            float ftop[K + 1], fbot[K + 1];
+            ftop[0] = fbot[0] = 0.f;
+#pragma unroll
+            for (int m = 1; m <= K; ++m) {
+                ftop[m] = ftop[m - 1] + full[m - 1];
+                fbot[m] = fbot[m - 1] + full[KW - m];
+            }
+#pragma unroll
+            for (int cb = 0; cb < NC; ++cb) {
+                // r[a] = the columns of row a that are out of area for column class cb
+                float r[KW];
+#pragma unroll
+                for (int a = 0; a < KW; ++a) r[a] = cb < K ? pre[a][K - cb] : (cb > K ? suf[a][cb - K] : 0.f);
+                // rows in area contribute r: sums of r over the rows below the top n / above the bottom n
+                float rlow[K + 1], rhigh[K + 1];   // rlow[n] = sum_{a >= n} r[a], rhigh[n] = sum_{a < KW - n} r[a]
+                float mid = r[K];
+#pragma unroll
+                for (int m = 1; m < K; ++m) mid += r[K - m] + r[K + m];          // rows 1..KW-2
+                // rows K..KW-1-... build from the middle outwards so that every partial is a plain sum
+                float all = (r[0] + mid) + r[KW - 1];
+                rlow[0] = all;
+                rhigh[0] = all;
+                {
+                    float t = 0.f;   // rlow[n]: drop the first n rows = sum of rows n..KW-1, accumulated from the bottom
+                    float sfx[KW + 1];
+                    sfx[KW] = 0.f;
+#pragma unroll
+                    for (int a = KW - 1; a >= 0; --a) sfx[a] = sfx[a + 1] + r[a];
+                    float pfx[KW + 1];
+                    pfx[0] = 0.f;
+#pragma unroll
+                    for (int a = 0; a < KW; ++a) pfx[a + 1] = pfx[a] + r[a];
+#pragma unroll
+                    for (int n = 1; n <= K; ++n) { rlow[n] = sfx[n]; rhigh[n] = pfx[KW - n]; }
+                    (void)t;
+                }
+#pragma unroll
+                for (int ca = 0; ca < NC; ++ca) {
+                    const int n_top = ca < K ? K - ca : 0, n_bot = ca > K ? ca - K : 0;
+                    // ca < K: the first n_top rows in full, the rest by r; ca > K: the last n_bot rows in full
+                    const float v = ca < K ? ftop[n_top] + rlow[n_top] : (ca > K ? fbot[n_bot] + rhigh[n_bot] : all);
+                    mine[ca * NC + cb] = v;
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < NC * NC; ++i) mine[i] = 0.f;
         }
-        __syncwarp();
+        __syncthreads();
+        const int n_here = min(kEoutThreads, slot1 - base);
+        float* dst = eout + (long long)base * (NC * NC);
+        for (int i = threadIdx.x; i < n_here * NC * NC; i += kEoutThreads) dst[i] = sOut[(i / (NC * NC)) * OP + i % (NC * NC)];
+        __syncthreads();
     }
 }
 
