@@ -487,23 +487,23 @@ extern "C" int ssl_b200_plane_rows_backward(const void* image, int dtype, int B,
 
 namespace {
 
-// [terms: sum|d|, sumKL, n_rows] -> loss[0..2] = total, w_l1*L1, w_kl*KL and inv_n = 1/(n_rows*L)
-__global__ void finalize_loss_kernel(const double* terms, int L, float w_l1, float w_kl, float* loss, float* inv_n) {
-    const double n_tot = fmax(terms[2] * (double)L, 1.0);
-    const double l1 = (double)w_l1 * terms[0] / n_tot, kl = (double)w_kl * terms[1] / n_tot;
-    loss[0] = (float)(l1 + kl);
-    loss[1] = (float)l1;
-    loss[2] = (float)kl;
-    *inv_n = (float)(1.0 / n_tot);
-}
-
-__global__ void __launch_bounds__(256) scale_kernel(float4* g, long long n4, const float* scale) {
-    const float s = *scale;
+__global__ void __launch_bounds__(256) scale_imm_kernel(float4* g, long long n4, float s) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = g[i];
         v.x *= s; v.y *= s; v.z *= s; v.w *= s;
         g[i] = v;
     }
+}
+
+// loss[0..2] = total, w_l1*L1, w_kl*KL from the terms of the (one or two) sub-batches and the host-known row count
+__global__ void finalize_loss_parts_kernel(const double* terms, int n_parts, double n_tot, float w_l1, float w_kl,
+                                           float* loss) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = 0; i < n_parts; ++i) { s0 += terms[4 * i]; s1 += terms[4 * i + 1]; }
+    const double l1 = (double)w_l1 * s0 / n_tot, kl = (double)w_kl * s1 / n_tot;
+    loss[0] = (float)(l1 + kl);
+    loss[1] = (float)l1;
+    loss[2] = (float)kl;
 }
 
 // terms[2] = number of rows.  An edge list that overflowed its capacity (counts[1] = pixels found >
@@ -698,7 +698,8 @@ struct HostArena {
     size_t bytes = 0;
     int32_t* counts_pinned = nullptr;
     cudaStream_t copy_stream = nullptr;   // carries the GT upload while the SR half of the forward runs
-    cudaEvent_t counted = nullptr, sr_sent = nullptr, gt_ready = nullptr;
+    cudaEvent_t counted = nullptr, sr_sent = nullptr, grad_ready = nullptr, gt_ready[2] = {nullptr, nullptr},
+                sr_ready[2] = {nullptr, nullptr};
 };
 
 HostArena& arena() {
@@ -722,7 +723,11 @@ int arena_reserve(size_t bytes) {
         SSLB_CUDA(cudaStreamCreateWithFlags(&a.copy_stream, cudaStreamNonBlocking));
         SSLB_CUDA(cudaEventCreateWithFlags(&a.counted, cudaEventDisableTiming));
         SSLB_CUDA(cudaEventCreateWithFlags(&a.sr_sent, cudaEventDisableTiming));
-        SSLB_CUDA(cudaEventCreateWithFlags(&a.gt_ready, cudaEventDisableTiming));
+        SSLB_CUDA(cudaEventCreateWithFlags(&a.grad_ready, cudaEventDisableTiming));
+        for (int h = 0; h < 2; ++h) {
+            SSLB_CUDA(cudaEventCreateWithFlags(&a.gt_ready[h], cudaEventDisableTiming));
+            SSLB_CUDA(cudaEventCreateWithFlags(&a.sr_ready[h], cudaEventDisableTiming));
+        }
     }
     SSLB_CUDA(cudaMalloc(&a.base, bytes));
     a.bytes = bytes;
@@ -742,19 +747,22 @@ extern "C" int ssl_b200_release_host_arena(void) {
     if (a.copy_stream) {
         cudaEventDestroy(a.counted);
         cudaEventDestroy(a.sr_sent);
-        cudaEventDestroy(a.gt_ready);
+        cudaEventDestroy(a.grad_ready);
+        for (int h = 0; h < 2; ++h) { cudaEventDestroy(a.gt_ready[h]); cudaEventDestroy(a.sr_ready[h]); }
         cudaStreamDestroy(a.copy_stream);
     }
     a = HostArena{};
     return 0;
 }
 
-// Timeline of one call (st = the caller's stream, cs = the arena's copy stream):
-//   st: mask -> device, count edge pixels, count -> host | SR -> device | pad SR, lists, Eout + forward of SR |
-//       (wait for GT) pad GT, Eout + forward of GT, row loss, backward, mean, results -> host
-//   cs:                                                   (after SR)  GT -> device
-// The host reads the 4-byte count (it sizes the rows workspace) while SR is still on the wire, and the upload of
-// GT hides behind the SR half of the forward.
+// Timeline of one call (st = the caller's stream, cs = the arena's copy stream).  A batch that runs on the plane
+// kernels is processed as two half-batches h0, h1 so that transfers hide behind arithmetic:
+//   st: mask -> device, count edge pixels per half, counts -> host | SR(h0) -> device |
+//       step(h0) [waits for GT(h0) after the SR half of its forward] | scale grad(h0) |
+//       step(h1) [after SR(h1); waits for GT(h1)] | scale grad(h1) | loss | loss, grad(h1) -> host
+//   cs: (after SR(h0))  GT(h0), SR(h1), GT(h1) -> device  ...  (after scale grad(h0))  grad(h0) -> host
+// The host reads the counts (they size the rows workspace and give the 1/N of the mean) while SR(h0) is still on
+// the wire.  Both halves share one workspace: they run back to back on st.
 extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_host, const float* mask_host,
                                        int mask_channels, int B, int C, int H, int W, int mask_stride, int ks, int kw,
                                        float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* loss_host,
@@ -763,14 +771,22 @@ extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_hos
     SSLB_REQUIRE(B >= 1 && mask_channels >= 1, "bad shape");
     if (int e = check_sizes(ks, kw, H, W, C)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
     const size_t n_px = (size_t)B * H * W, img_bytes = align256(n_px * C * sizeof(float));
     SSLB_REQUIRE(n_px < (1ull << 31), "batch too large for int32 pixel indices");
     const size_t mask_bytes = align256(n_px * mask_channels * sizeof(float));
-    const size_t small_bytes = 256;  // terms double[3] | loss float[3] | inv_n float | count int32
+    const size_t small_bytes = 512;  // terms double[2][4] | loss float[3] | counts int32[2]
     const size_t fixed = 3 * img_bytes + mask_bytes + small_bytes;
+    // two halves when the batch can be split and the plane kernels exist for it
+    // (the halves of the gradient are scaled as float4: the split must fall on a 16-byte boundary)
+    const int n_parts = (B >= 2 && plane_supported(ks, kw, C) && ((size_t)(B / 2) * H * W * C) % 4 == 0) ? 2 : 1;
+    const int Bh[2] = {n_parts == 2 ? B / 2 : B, n_parts == 2 ? B - B / 2 : 0};
     // first pass with the arena we have (or a guess of one edge pixel in eight); rows need the edge count
     HostArena& a = arena();
-    if (int e = arena_reserve(fixed + ssl_b200_loss_step_workspace_bytes(B, C, H, W, ks, kw, (int)(n_px / 8 + 1), 0))) return e;
+    if (int e = arena_reserve(fixed + ssl_b200_loss_step_workspace_bytes(Bh[n_parts - 1], C, H, W, ks, kw,
+                                                                        (int)((size_t)Bh[n_parts - 1] * H * W / 8 + 1), 0)))
+        return e;
     auto carve = [&](char*& p, size_t b) { char* r = p; p += b; return r; };
     char* p = a.base;
     float* d_mask = (float*)carve(p, mask_bytes);
@@ -779,72 +795,101 @@ extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_hos
     float* d_gt = (float*)carve(p, img_bytes);
     float* d_grad = (float*)carve(p, img_bytes);
     char* d_ws = p;
-    double* d_terms = (double*)d_small;
-    float* d_loss = (float*)(d_small + 64);
-    float* d_inv_n = (float*)(d_small + 128);
-    int32_t* d_count = (int32_t*)(d_small + 192);
-    // mask first, so the edge count comes back while the images are still on the wire
+    double* d_terms = (double*)d_small;            // [2][4]
+    float* d_loss = (float*)(d_small + 256);
+    int32_t* d_count = (int32_t*)(d_small + 384);  // [2]
+    const size_t px_img = (size_t)H * W;
+    const size_t off_px[2] = {0, (size_t)Bh[0] * px_img};   // first pixel of each half
+    // mask first, so the edge counts come back while the images are still on the wire
     SSLB_CUDA(cudaMemcpyAsync(d_mask, mask_host, n_px * mask_channels * sizeof(float), cudaMemcpyHostToDevice, st));
-    SSLB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int32_t), st));
+    SSLB_CUDA(cudaMemsetAsync(d_count, 0, 2 * sizeof(int32_t), st));
     {
-        DeviceInfo di;
-        if (int e = device_info(&di)) return e;
-        EdgeListParams ep{};
-        ep.mask = d_mask; ep.mask_channels = mask_channels; ep.H = H; ep.W = W; ep.stride = mask_stride;
-        ep.n_pixels = (long long)n_px;
         StageTimer timer(kStageEdgeList, st);
-        mask_count_kernel<<<di.sm_count * 4, kElThreads, 0, st>>>(ep, d_count);
-        if (int e = check_launch("mask_count")) return e;
+        for (int h = 0; h < n_parts; ++h) {
+            EdgeListParams ep{};
+            ep.mask = d_mask + off_px[h] * mask_channels; ep.mask_channels = mask_channels; ep.H = H; ep.W = W;
+            ep.stride = mask_stride;
+            ep.n_pixels = (long long)Bh[h] * px_img;
+            mask_count_kernel<<<di.sm_count * 2, kElThreads, 0, st>>>(ep, d_count + h);
+        }
+        if (int e = check_launch("mask_count", n_parts)) return e;
     }
-    SSLB_CUDA(cudaMemcpyAsync(a.counts_pinned, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SSLB_CUDA(cudaMemcpyAsync(a.counts_pinned, d_count, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SSLB_CUDA(cudaEventRecord(a.counted, st));
-    SSLB_CUDA(cudaMemcpyAsync(d_sr, sr_host, n_px * C * sizeof(float), cudaMemcpyHostToDevice, st));
+    SSLB_CUDA(cudaMemcpyAsync(d_sr, sr_host, (size_t)Bh[0] * px_img * C * sizeof(float), cudaMemcpyHostToDevice, st));
     SSLB_CUDA(cudaEventRecord(a.sr_sent, st));
-    // GT follows SR on the copy stream (not beside it: SR is on the critical path)
+    // everything else follows on the copy stream, in the order it is needed (not beside SR(h0): that one is on the
+    // critical path)
     SSLB_CUDA(cudaStreamWaitEvent(a.copy_stream, a.sr_sent, 0));
-    SSLB_CUDA(cudaMemcpyAsync(d_gt, gt_host, n_px * C * sizeof(float), cudaMemcpyHostToDevice, a.copy_stream));
-    SSLB_CUDA(cudaEventRecord(a.gt_ready, a.copy_stream));
+    for (int h = 0; h < n_parts; ++h) {
+        const size_t o = off_px[h] * C, n = (size_t)Bh[h] * px_img * C;
+        if (h > 0) {
+            SSLB_CUDA(cudaMemcpyAsync(d_sr + o, sr_host + o, n * sizeof(float), cudaMemcpyHostToDevice, a.copy_stream));
+            SSLB_CUDA(cudaEventRecord(a.sr_ready[h], a.copy_stream));
+        }
+        SSLB_CUDA(cudaMemcpyAsync(d_gt + o, gt_host + o, n * sizeof(float), cudaMemcpyHostToDevice, a.copy_stream));
+        SSLB_CUDA(cudaEventRecord(a.gt_ready[h], a.copy_stream));
+    }
     cudaError_t ce = cudaEventSynchronize(a.counted);
     if (ce != cudaSuccess) return fail((int)ce, "edge count readback: %s", cudaGetErrorString(ce));
-    const int n_rows = a.counts_pinned[0];
-    const size_t ws_bytes = ssl_b200_loss_step_workspace_bytes(B, C, H, W, ks, kw, n_rows, 0);
+    const int n_half[2] = {a.counts_pinned[0], n_parts == 2 ? a.counts_pinned[1] : 0};
+    const long long n_rows = (long long)n_half[0] + n_half[1];
+    size_t ws_bytes = 0;
+    for (int h = 0; h < n_parts; ++h) {
+        const size_t w = ssl_b200_loss_step_workspace_bytes(Bh[h], C, H, W, ks, kw, n_half[h], 0);
+        ws_bytes = w > ws_bytes ? w : ws_bytes;
+    }
     if (fixed + ws_bytes > a.bytes) {
         // grow (rare: first call, or a denser mask than ever seen) and redo the uploads
         SSLB_CUDA(cudaStreamSynchronize(a.copy_stream));
+        SSLB_CUDA(cudaStreamSynchronize(st));
         if (int e = arena_reserve(fixed + ws_bytes + ws_bytes / 4)) return e;
         return ssl_b200_loss_step_host(sr_host, gt_host, mask_host, mask_channels, B, C, H, W, mask_stride, ks, kw,
                                        sigma, eps, rows_mode, w_l1, w_kl, loss_host, grad_host, n_rows_host, stream);
     }
-    {
+    const double n_tot = n_rows > 0 ? (double)n_rows * ks * ks : 1.0;
+    const float inv_n = (float)(1.0 / n_tot);
+    for (int h = 0; h < n_parts; ++h) {
+        const size_t o = off_px[h] * C;
         StepInputs in{};
-        in.sr = d_sr; in.gt = d_gt; in.dtype_sr = SSL_B200_F32; in.dtype_gt = SSL_B200_F32;
-        in.mask = d_mask; in.mask_channels = mask_channels; in.mask_stride = mask_stride;
-        const bool plane = n_rows > 0 && use_plane_path(SSL_B200_PATH_AUTO, B, C, H, W, ks, kw, n_rows);
+        in.sr = d_sr + o; in.gt = d_gt + o; in.dtype_sr = SSL_B200_F32; in.dtype_gt = SSL_B200_F32;
+        in.mask = d_mask + off_px[h] * mask_channels; in.mask_channels = mask_channels; in.mask_stride = mask_stride;
+        float* grad_h = grad_host ? d_grad + o : nullptr;
+        double* terms_h = d_terms + 4 * h;
+        if (h > 0) SSLB_CUDA(cudaStreamWaitEvent(st, a.sr_ready[h], 0));
+        const bool plane = n_half[h] > 0 && use_plane_path(SSL_B200_PATH_AUTO, Bh[h], C, H, W, ks, kw, n_half[h]);
         int rc;
         if (plane) {
-            in.gt_ready = a.gt_ready;   // the step waits for GT itself, after the SR half of the forward
-            rc = loss_step_impl(in, nullptr, B, C, H, W, n_rows, ks, kw, sigma, eps, rows_mode, w_l1, w_kl,
-                                grad_host ? d_grad : nullptr, d_terms, d_ws, ws_bytes, SSL_B200_PATH_AUTO, st);
+            in.gt_ready = a.gt_ready[h];   // the step waits for GT itself, after the SR half of the forward
+            rc = loss_step_impl(in, nullptr, Bh[h], C, H, W, n_half[h], ks, kw, sigma, eps, rows_mode, w_l1, w_kl, grad_h,
+                                terms_h, d_ws, ws_bytes, SSL_B200_PATH_AUTO, st);
         } else {
-            SSLB_CUDA(cudaStreamWaitEvent(st, a.gt_ready, 0));
-            rc = ssl_b200_loss_step(d_sr, SSL_B200_F32, d_gt, SSL_B200_F32, d_mask, mask_channels, mask_stride, B, C, H, W,
-                                    n_rows, ks, kw, sigma, eps, rows_mode, w_l1, w_kl, grad_host ? d_grad : nullptr,
-                                    d_terms, d_ws, ws_bytes, SSL_B200_PATH_AUTO, stream);
+            SSLB_CUDA(cudaStreamWaitEvent(st, a.gt_ready[h], 0));
+            rc = ssl_b200_loss_step(in.sr, SSL_B200_F32, in.gt, SSL_B200_F32, in.mask, mask_channels, mask_stride, Bh[h],
+                                    C, H, W, n_half[h], ks, kw, sigma, eps, rows_mode, w_l1, w_kl, grad_h, terms_h, d_ws,
+                                    ws_bytes, SSL_B200_PATH_AUTO, stream);
         }
         if (rc) return rc;
+        if (grad_host) {
+            const size_t n = (size_t)Bh[h] * px_img * C;   // a multiple of 4 for all but degenerate shapes
+            const long long n4 = (long long)((n + 3) / 4);  // the tail of the last half runs into our own padding
+            scale_imm_kernel<<<di.sm_count * 4, 256, 0, st>>>((float4*)(d_grad + o), n4, inv_n);
+            if (int e = check_launch("scale_grad")) return e;
+            if (h + 1 < n_parts) {
+                // the first half's gradient goes home on the copy stream while the second half is computed
+                SSLB_CUDA(cudaEventRecord(a.grad_ready, st));
+                SSLB_CUDA(cudaStreamWaitEvent(a.copy_stream, a.grad_ready, 0));
+                SSLB_CUDA(cudaMemcpyAsync(grad_host + o, d_grad + o, n * sizeof(float), cudaMemcpyDeviceToHost, a.copy_stream));
+            } else {
+                SSLB_CUDA(cudaMemcpyAsync(grad_host + o, d_grad + o, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+            }
+        }
     }
-    finalize_loss_kernel<<<1, 1, 0, st>>>(d_terms, ks * ks, w_l1, w_kl, d_loss, d_inv_n);
+    finalize_loss_parts_kernel<<<1, 1, 0, st>>>(d_terms, n_parts, n_tot, w_l1, w_kl, d_loss);
     if (int e = check_launch("finalize_loss")) return e;
     SSLB_CUDA(cudaMemcpyAsync(loss_host, d_loss, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (grad_host) {
-        const long long n4 = (long long)(img_bytes / sizeof(float4));  // the pad is ours: scale whole float4s
-        DeviceInfo di;
-        if (int e = device_info(&di)) return e;
-        scale_kernel<<<di.sm_count * 8, 256, 0, st>>>((float4*)d_grad, n4, d_inv_n);
-        if (int e = check_launch("scale_grad")) return e;
-        SSLB_CUDA(cudaMemcpyAsync(grad_host, d_grad, n_px * C * sizeof(float), cudaMemcpyDeviceToHost, st));
-    }
     SSLB_CUDA(cudaStreamSynchronize(st));
+    SSLB_CUDA(cudaStreamSynchronize(a.copy_stream));
     if (n_rows_host) *n_rows_host = n_rows;
     return 0;
 }
