@@ -183,6 +183,13 @@ int ssl_b200_loss_step(const void* sr, int dtype_sr, const void* gt, int dtype_g
                        float sigma, float eps, int rows_mode, float w_l1, float w_kl, float* grad_sr, double* terms,
                        void* workspace, size_t workspace_bytes, int path, void* stream);
 
+/* The 'mean' of the step: terms (double [3]: sum|d|, sum KL, n_rows -- local, or all-reduced over the ranks) ->
+ * out4 (float [4]) = { w_l1*L1 + w_kl*KL, w_l1*L1, w_kl*KL, grad_scale / N } with N = max(n_rows * row_len, 1); the last
+ * entry is the factor the gradient returned by the step is multiplied with.  A NaN row count (overflowed edge
+ * list) makes all four NaN. */
+int ssl_b200_loss_from_terms(const double* terms, int row_len, float w_l1, float w_kl, float grad_scale, float* out4,
+                             void* stream);
+
 /* Test / inspection hook: dL/dq (the gradient with respect to the raw patch distances, before the 1/N of the
  * 'mean') that the last ssl_b200_loss_forward_backward call with a non-NULL grad_sr left in `workspace`,
  * copied out as fp32 rows [n, ks*ks] in the order of `edges`.  Same shape arguments as that call. */

@@ -60,6 +60,7 @@ SIGNATURES = {
     "ssl_b200_loss_step": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                     _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_float,
                                     _c_float, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_void_p]),
+    "ssl_b200_loss_from_terms": (_c_int, [_c_void_p, _c_int, _c_float, _c_float, _c_float, _c_void_p, _c_void_p]),
     "ssl_b200_loss_export_distance_grad": (_c_int, [_c_void_p, _c_size_t, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                                     _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "ssl_b200_loss_step_host": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,

@@ -894,6 +894,25 @@ extern "C" int ssl_b200_loss_step_host(const float* sr_host, const float* gt_hos
     return 0;
 }
 
+namespace {
+__global__ void loss_from_terms_kernel(const double* terms, int L, float w_l1, float w_kl, float grad_scale, float* out) {
+    const double n_tot = fmax(terms[2] * (double)L, 1.0);   // NaN (poisoned count) propagates: fmax(NaN, 1) = 1 is avoided below
+    const double n = terms[2] != terms[2] ? terms[2] : n_tot;
+    const double l1 = (double)w_l1 * terms[0] / n, kl = (double)w_kl * terms[1] / n;
+    out[0] = (float)(l1 + kl);
+    out[1] = (float)l1;
+    out[2] = (float)kl;
+    out[3] = (float)((double)grad_scale / n);
+}
+}  // namespace
+
+extern "C" int ssl_b200_loss_from_terms(const double* terms, int row_len, float w_l1, float w_kl, float grad_scale,
+                                        float* out4, void* stream) {
+    SSLB_REQUIRE(terms && out4 && row_len >= 1, "bad arguments");
+    loss_from_terms_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(terms, row_len, w_l1, w_kl, grad_scale, out4);
+    return check_launch("loss_from_terms");
+}
+
 // ---- crop + training-pair pool -------------------------------------------------
 
 extern "C" int ssl_b200_crop(const void* src, void* dst, int planes, int H, int W, int top, int left, int h, int w,

@@ -281,14 +281,13 @@ class _SSLLoss(torch.autograd.Function):
                       ws_bytes, int(path), _stream())
         if reducer is not None:
             terms = reducer(terms)
-        n_tot = (terms[2] * (ks * ks)).clamp_min(1.0)
-        l1 = terms[0] / n_tot
-        kl = terms[1] / n_tot
-        total = (w_l1 * l1 + w_kl * kl).to(torch.float32)
-        part_l1 = (w_l1 * l1).to(torch.float32)
-        part_kl = (w_kl * kl).to(torch.float32)
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)   # total, l1 part, kl part, gradient factor
+        with torch.cuda.device(dev):
+            _lib.call("ssl_b200_loss_from_terms", _ptr(terms), ks * ks, float(w_l1), float(w_kl), float(grad_scale),
+                      _ptr(out4), _stream())
+        total, part_l1, part_kl = out4[0], out4[1], out4[2]
         ctx.grad_sr = grad
-        ctx.inv_n = (grad_scale / n_tot).to(torch.float32)
+        ctx.inv_n = out4[3]
         ctx.sr_dtype = sr.dtype
         ctx.mark_non_differentiable(part_l1, part_kl)  # logging values; `total` carries the gradient
         return total, part_l1, part_kl
