@@ -1,4 +1,4 @@
-// Backward "plane" kernels: dL/dimage from dL/dq held offset-major (gqT[d][slot]).
+// Backward "plane" kernels: dL/dimage from dL/dq held in the rows buffer (panel layout, plane_geom.cuh: qt_index).
 //
 // Adjoint of ssg_plane_fwd.cuh, in gather form (no global atomics, fixed summation order).  For a
 // search offset d the contributions of all edge pixels are first spread into a sparse plane
@@ -11,9 +11,10 @@
 // the neighbour role of x, re-indexed so that it is gathered at x too).  tests/dense_model.py holds
 // the NumPy statement of these placement rules.
 //
-// One CTA = one 64 x TXB tile of the PADDED image and one dx-group; its NWP workers (warp pairs,
-// lane = image row) take dy = w, w+NWP, ... and free-run; additions into the shared accumulator tile
-// are ordered by per-chunk tickets (deterministic summation order, no atomics).
+// One CTA = one 32 x TXB tile of the PADDED image (its image window arrives by one TMA tensor copy) and one
+// dx-group; its NWP = 12 workers (single warps, lane = image row) take dy = w - P, w - P + NWP and one output chunk
+// of the left-over dy, and free-run; the partial sums go into accumulator tiles held in tensor memory (TMEM, one
+// per lane quarter), additions ordered by per-chunk tickets (deterministic summation order, no atomics on data).
 #pragma once
 
 #include <cuda/atomic>
