@@ -523,7 +523,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(const __
     const bool staged = n_ent <= BC::LIST_SMEM;
     if (staged)
         for (int i = threadIdx.x; i < n_ent; i += blockDim.x) ent_s[i] = ent_g[i];
-    const int32_t* ent = staged ? ent_s : ent_g;
     __syncthreads();
     uint32_t tmem_base = 0;
 #if SSLB_BWD_TMEM
@@ -540,16 +539,22 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(const __
     tmem_fence_after_sync();
 #endif
     mbar_wait(&tile_bar, 0);
-    switch (blockIdx.y) {
-        case 0: run_group_bwd<Cfg, 0>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
-        case 1: if constexpr (Cfg::NDXG > 1) run_group_bwd<Cfg, 1>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
-        case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
-        case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
-        case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
-        case 5: if constexpr (Cfg::NDXG > 5) run_group_bwd<Cfg, 5>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
-        case 6: if constexpr (Cfg::NDXG > 6) run_group_bwd<Cfg, 6>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
-        default: break;
-    }
+    // two copies of the dispatch: with the entry list staged (always, below ~35 % mask density) the compiler sees a
+    // shared-memory pointer and emits LDS instead of generic loads
+    auto dispatch = [&](const int32_t* ent) {
+        switch (blockIdx.y) {
+            case 0: run_group_bwd<Cfg, 0>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+            case 1: if constexpr (Cfg::NDXG > 1) run_group_bwd<Cfg, 1>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+            case 2: if constexpr (Cfg::NDXG > 2) run_group_bwd<Cfg, 2>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+            case 3: if constexpr (Cfg::NDXG > 3) run_group_bwd<Cfg, 3>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+            case 4: if constexpr (Cfg::NDXG > 4) run_group_bwd<Cfg, 4>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+            case 5: if constexpr (Cfg::NDXG > 5) run_group_bwd<Cfg, 5>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+            case 6: if constexpr (Cfg::NDXG > 6) run_group_bwd<Cfg, 6>(p, tile, ubuf, accT, cols_s, cum_s, ent, turn_s, tmem_base); break;
+            default: break;
+        }
+    };
+    if (staged) dispatch(ent_s);
+    else dispatch(ent_g);
 #if SSLB_BWD_TMEM
     // the four quarter accumulators are added into the (zeroed) shared tile in quarter order, then TMEM is released
     tmem_fence_before_sync();
