@@ -155,3 +155,40 @@ def test_overflowing_edge_list_poisons_the_loss(dev):
     x2 = sr.to(dev).requires_grad_(True)
     ok = ssl(x2, gt.to(dev), mask.to(dev), 11, 5, max_edges=n)
     assert torch.isfinite(ok)
+
+
+def test_diffusion_crop_shape_with_mask_stride(dev):
+    """BASELINE configs[4] shape: a 400x400 crop, dense (34 %) mask thinned by mask_stride = 3 as the diffusion
+    config does (ddpmssl.py:445-446), eps = 1e-20 as its shipped strategy (loss_util.py:1250) -- through ssl()."""
+    from ssl_b200 import ssl, synth
+    sr, gt, mask = synth.make_case(1, 400, 400, seed=4, density=0.344)
+    l1, _, grad, n = oracle.loss_and_grad(sr.numpy().astype(np.float64), gt.numpy().astype(np.float64), mask.numpy(), KS,
+                                          KW, SIGMA, True, eps=1e-20, loss_weight=5e2, mask_stride=3)
+    x = sr.to(dev).requires_grad_(True)
+    loss = ssl(x, gt.to(dev), mask.to(dev), KS, KW, SIGMA, True, eps=1e-20, loss_weight=5e2, mask_stride=3)
+    loss.backward()
+    assert float(loss.detach()) == pytest.approx(l1, rel=1e-5)
+    d = np.abs(x.grad.cpu().numpy() - grad) / np.abs(grad).max()
+    # whole-gradient comparison is tie-aware (module docstring): nearly all pixels to 1e-5, none off by more than a flip
+    assert np.quantile(d, 0.9) <= 1e-5 and d.max() <= 5e-3
+
+
+def test_mixed_precision_inputs_keep_the_target_exact(dev):
+    """bf16 SR (autocast) against an fp32 GT on the plane path: GT is NOT rounded to bf16 -- the result
+    equals the oracle on (bf16-rounded SR, exact GT) and differs from the one with a rounded GT."""
+    from ssl_b200 import ssl, synth
+    sr, gt, mask = synth.make_case(2, 64, 72, seed=9, density=0.15)
+    sr_b = sr.bfloat16()
+    want, _, _, _ = oracle.loss_and_grad(sr_b.double().numpy(), gt.double().numpy(), mask.numpy(), 11, 5, SIGMA, True)
+    rounded, _, _, _ = oracle.loss_and_grad(sr_b.double().numpy(), gt.bfloat16().double().numpy(), mask.numpy(), 11, 5,
+                                            SIGMA, True)
+    x = sr_b.to(dev).requires_grad_(True)
+    loss = ssl(x, gt.to(dev), mask.to(dev), 11, 5, SIGMA, True, path="plane")
+    loss.backward()
+    assert float(loss.detach()) == pytest.approx(want, rel=1e-5)
+    assert abs(rounded - want) > 1e-4 * want          # the test has teeth: rounding GT would be 10x the tolerance
+    assert x.grad.dtype == torch.bfloat16
+    # point kernels take one element type: both images are upcast, with the same result
+    x2 = sr_b.to(dev).requires_grad_(True)
+    loss2 = ssl(x2, gt.to(dev), mask.to(dev), 11, 5, SIGMA, True, path="point")
+    assert float(loss2.detach()) == pytest.approx(want, rel=1e-5)
