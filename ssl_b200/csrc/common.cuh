@@ -101,6 +101,32 @@ struct StageTimer {
         if (e_ != cudaSuccess) return sslb::fail((int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// A second stream of the calling thread on the current device, for small kernels that do not lie on the step's
+// critical path (list building next to the padding, the backward's tile lists next to the forward).  Work is
+// forked from / joined into the caller's stream with events only, so a step stays capturable into a CUDA graph.
+// One lane per (thread, device): the fork / join events are never shared between two callers.
+struct SideLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+};
+
+inline int side_lane(SideLane** out) {
+    constexpr int kMaxDev = 64;
+    static thread_local SideLane lanes[kMaxDev];
+    int dev = 0;
+    SSLB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) return sslb::fail(SSL_B200_EINVAL, "device ordinal %d out of range", dev);
+    SideLane& l = lanes[dev];
+    if (!l.stream) {
+        SSLB_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        SSLB_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+        SSLB_CUDA(cudaEventCreateWithFlags(&l.join[0], cudaEventDisableTiming));
+        SSLB_CUDA(cudaEventCreateWithFlags(&l.join[1], cudaEventDisableTiming));
+    }
+    *out = &l;
+    return 0;
+}
+
 struct DeviceInfo {
     int sm_count = 0;
     int max_smem_optin = 0;

@@ -210,26 +210,46 @@ inline PlaneStepLayout plane_step_layout(int B, int H, int W, int max_edges, int
 // rows backward of the operator API.  `pad` = reflect-padded fp32 image the gradient is taken for.
 // grad_out == NULL: stop after the fold -- the padded-domain gradient stays in part 0 of gpart (ws + l.off_gpart).
 template <typename Cfg>
-inline int launch_plane_backward_cfg(const float* pad, int B, int H, int W, const PlaneLists& lists,
-                                     const PlaneStepLayout& l, char* ws, const float* gqT, const float* gcls,
-                                     float* grad_out, cudaStream_t st) {
-    using BG = PlaneBwdGeom<Cfg>;
-    DeviceInfo di;
-    if (int e = device_info(&di)) return e;
+inline PlaneBwdParams plane_bwd_params(int B, int H, int W, const PlaneLists& lists, const PlaneStepLayout& l, char* ws,
+                                       const float* gqT) {
     PlaneBwdParams bp{};
     bp.gqT = gqT;
-    int32_t* tcols = reinterpret_cast<int32_t*>(ws + l.off_tcols);
-    uint8_t* tcum = reinterpret_cast<uint8_t*>(ws + l.off_tcum);
-    int32_t* tent = reinterpret_cast<int32_t*>(ws + l.off_tent);
-    bp.tile_cols = tcols; bp.tile_cum = tcum; bp.tile_ent = tent;
+    bp.tile_cols = reinterpret_cast<int32_t*>(ws + l.off_tcols);
+    bp.tile_cum = reinterpret_cast<uint8_t*>(ws + l.off_tcum);
+    bp.tile_ent = reinterpret_cast<int32_t*>(ws + l.off_tent);
     bp.gpart = reinterpret_cast<float*>(ws + l.off_gpart);
     bp.slot_map = lists.slot_map;
     bp.B = B; bp.H = H; bp.W = W; bp.cap = l.cap;
     bp.ntyb = l.ntyb; bp.ntxb = l.ntxb; bp.HT = l.HT; bp.WT = l.WT;
+    return bp;
+}
+
+// Per-tile column lists of the backward: a function of the slot lists only (not of dL/dq), so the fused step
+// builds them on its side lane while the forward runs.
+template <typename Cfg>
+inline int launch_plane_bwd_lists_cfg(int B, int H, int W, const PlaneLists& lists, const PlaneStepLayout& l, char* ws,
+                                      cudaStream_t st) {
+    using BG = PlaneBwdGeom<Cfg>;
+    const PlaneBwdParams bp = plane_bwd_params<Cfg>(B, H, W, lists, l, ws, nullptr);
     {
         StageTimer timer(kStagePlaneBwdLists, st);
-        plane_bwd_lists_kernel<BG><<<l.n_btiles, 256, 0, st>>>(bp, tcols, tcum, tent);
+        plane_bwd_lists_kernel<BG><<<l.n_btiles, 256, 0, st>>>(bp, const_cast<int32_t*>(bp.tile_cols),
+                                                               const_cast<uint8_t*>(bp.tile_cum),
+                                                               const_cast<int32_t*>(bp.tile_ent));
     }
+    return check_launch("plane_bwd_lists");
+}
+
+template <typename Cfg>
+inline int launch_plane_backward_cfg(const float* pad, int B, int H, int W, const PlaneLists& lists,
+                                     const PlaneStepLayout& l, char* ws, const float* gqT, const float* gcls,
+                                     float* grad_out, cudaStream_t st, bool tile_lists_built = false) {
+    using BG = PlaneBwdGeom<Cfg>;
+    DeviceInfo di;
+    if (int e = device_info(&di)) return e;
+    const PlaneBwdParams bp = plane_bwd_params<Cfg>(B, H, W, lists, l, ws, gqT);
+    if (!tile_lists_built)
+        if (int e = launch_plane_bwd_lists_cfg<Cfg>(B, H, W, lists, l, ws, st)) return e;
     const size_t smem = plane_bwd_smem_bytes<BG>();
     SSLB_REQUIRE(smem <= (size_t)di.max_smem_optin, "plane backward needs %zu B of shared memory", smem);
     CUtensorMap tmap;
@@ -278,14 +298,25 @@ inline int launch_plane_step_cfg(const StepInputs& in, int B, int H, int W, int 
     char* ws = static_cast<char*>(workspace);
     float* pad = reinterpret_cast<float*>(ws + l.off_pad);
     float* pad_gt = pad + l.pad.bytes_per_image_set / sizeof(float);
+    // Side lane: the slot lists (next to the padding) and then the backward's tile lists (next to the forward) --
+    // both depend on the mask only.  join[0] = slot lists ready, join[1] = tile lists ready.
+    SideLane* side = nullptr;
+    if (int e = side_lane(&side)) return e;
+    SSLB_CUDA(cudaEventRecord(side->fork, st));
+    SSLB_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    if (int e = launch_plane_lists(in.mask, in.mask_channels, in.mask_stride, in.edges, in.n_edges_dev, max_edges, l.g,
+                                   l.cap, ws, side->stream, Cfg::SRP, 32 / Cfg::G)) return e;
+    SSLB_CUDA(cudaEventRecord(side->join[0], side->stream));
+    const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
+    if (grad_sr)
+        if (int e = launch_plane_bwd_lists_cfg<Cfg>(B, H, W, lists, l, ws, side->stream)) return e;
+    SSLB_CUDA(cudaEventRecord(side->join[1], side->stream));
     if (in.gt_ready) {
         if (int e = launch_pad(in.sr, in.dtype_sr, nullptr, in.dtype_sr, B, H, W, Cfg::P, pad, st)) return e;
     } else {
         if (int e = launch_pad(in.sr, in.dtype_sr, in.gt, in.dtype_gt, B, H, W, Cfg::P, pad, st)) return e;
     }
-    if (int e = launch_plane_lists(in.mask, in.mask_channels, in.mask_stride, in.edges, in.n_edges_dev, max_edges, l.g,
-                                   l.cap, ws, st, Cfg::SRP, 32 / Cfg::G)) return e;
-    const PlaneLists lists = carve_lists(ws, l.lists, nullptr);
+    SSLB_CUDA(cudaStreamWaitEvent(st, side->join[0], 0));
     if (in.mask) {
         plane_terms_count_kernel<<<1, 1, 0, st>>>(lists.counts, max_edges, l.cap, terms);
         if (int e = check_launch("plane_terms_count")) return e;
@@ -322,8 +353,9 @@ inline int launch_plane_step_cfg(const StepInputs& in, int B, int H, int W, int 
         rl_kernel<<<loss_blocks, kRowTThreads, rl_smem, st>>>(rp);
     }
     if (int e = check_launch("row_loss_t", 1)) return e;
+    SSLB_CUDA(cudaStreamWaitEvent(st, side->join[1], 0));   // always: the side lane rejoins the caller's stream
     if (!grad_sr) return 0;
-    return launch_plane_backward_cfg<Cfg>(pad, B, H, W, lists, l, ws, q_sr, nullptr, grad_sr, st);
+    return launch_plane_backward_cfg<Cfg>(pad, B, H, W, lists, l, ws, q_sr, nullptr, grad_sr, st, true);
 }
 
 // dL/dq rows in the order of `edges` [n][L] -> padded-domain (grad == NULL, result in part 0 of gpart) or image-domain
