@@ -234,3 +234,17 @@ def test_step_is_cuda_graph_capturable(dev):
         assert torch.isfinite(got_loss) and float(got_loss) > 0
         assert torch.equal(got_loss, want_loss.detach())
         assert torch.equal(got_grad, want_grad)
+
+
+@pytest.mark.parametrize("density", [0.6, 1.0])
+def test_dense_masks_take_the_unstaged_list_paths(dev, density):
+    """Above ~36 % (backward: 2,560 entries per tile) and ~57 % (forward: 2,048 slots per tile) mask density the
+    tile lists no longer fit the shared-memory staging areas and the kernels read them from global memory; columns
+    hold more than 8 entries per kind (batched placement).  Every stage strictly, as at the benchmark shape."""
+    from ssl_b200 import synth
+    sr, gt, mask = synth.make_case(1, 72, 104, seed=31, density=density)
+    if density == 1.0:
+        assert int(mask.sum()) == 72 * 104
+    loss, grad, gq, n, pos = fused_step_with_export(dev, sr, gt, mask, path=2)
+    assert n == int(mask.sum())
+    check_stages(sr, gt, mask, loss, grad, gq, pos, min_clean=0.05)
