@@ -50,19 +50,35 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// sum of N partials (stride apart) as a balanced tree: log2 N dependent additions instead of N
+template <int N>
+__device__ __forceinline__ float tree_sum(const float* v, int stride) {
+    static_assert((N & (N - 1)) == 0, "power of two");
+    float t[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) t[k] = v[k * stride];
+#pragma unroll
+    for (int w = 1; w < N; w *= 2)
+#pragma unroll
+        for (int k = 0; k + w < N; k += 2 * w) t[k] += t[k + w];
+    return t[0];
+}
+
 template <int KS, int KW, bool HAS_KL>
 __global__ void __launch_bounds__(kRowTThreads, 2) row_loss_t_kernel(RowLossTParams p) {
     extern __shared__ __align__(16) float gqbuf[];           // [L][NS] dL/dq of the current group (pass 4)
     constexpr int NS = kRowTSlots, NPH = kRowTPhases;
     constexpr int L = KS * KS, P = KS / 2, K = KW / 2, NC = 2 * K + 1;
     const int cap = p.cap, mode = p.mode;
-    __shared__ float red[2][NPH][NS];
+    constexpr int NWARP = kRowTThreads / 32;
+    __shared__ float red[2][NWARP][NS];             // a warp = two phases x 16 slots: one partial per (warp, slot)
     __shared__ float sG[NC * NC][NS], sT[NC * KW][NS], sR[NC][NS], sW[NS * KW * KW];
     __shared__ double dred[32];
     __shared__ int last_flag;
     const int n_slots = min(p.counts[0], cap);
     const int n_groups = (n_slots + NS - 1) / NS;
     const int s = threadIdx.x % NS, ph = threadIdx.x / NS;
+    const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
     // e = exp(-1 * (q / (C kw^2)) / sigma) of loss_util.py:224-225 as 2^(q * nscale2): the two divisions and the
     // change of base are folded into one constant (computed in double), so the argument is rounded once
     const float nscale2 = (float)(-1.4426950408889634 / ((double)p.denom * (double)p.sigma));
@@ -73,23 +89,27 @@ __global__ void __launch_bounds__(kRowTThreads, 2) row_loss_t_kernel(RowLossTPar
     const bool has_tail = ph < L - NFULL * NPH;       // and the first L mod NPH phases one more
     constexpr int NV = NFULL + 1;
     double l1_tot = 0.0, kl_tot = 0.0;
+    // The thread's ~20 (slot, offset) pairs are loaded straight into registers -- 2 * NV independent loads in
+    // flight per thread, every warp instruction two full 64-byte segments -- and stay there through all
+    // passes; shared memory only carries the row reductions and dL/dq for the class sums of pass 4.  The loads of
+    // the block's NEXT group are issued as soon as the registers are free (after pass 3), so they fly during pass 4.
+    float vs[NV], vt[NV];
+    bool valid = false;
+    auto fetch = [&](int g) {
+        const int slot = g * NS + s;
+        valid = g < n_groups && slot < n_slots && p.slot_pix[slot] >= 0;
+        const float* gs = p.qs + qt_index(ph, slot, L);   // the group is one panel: L * 64 contiguous bytes
+        const float* gg = p.qg + qt_index(ph, slot, L);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const bool on = valid && (i < NFULL || has_tail);
+            vs[i] = on ? __ldcs(gs + i * gstride) : 0.f;
+            vt[i] = on ? __ldcs(gg + i * gstride) : 0.f;
+        }
+    };
+    fetch(blockIdx.x);
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const int slot = g * NS + s;
-        const bool valid = slot < n_slots && p.slot_pix[slot] >= 0;
-        // The thread's ~20 (slot, offset) pairs are loaded straight into registers -- 2 * NV independent loads in
-        // flight per thread, every warp instruction two full 64-byte segments -- and stay there through all
-        // passes; shared memory only carries the row reductions and dL/dq for the class sums of pass 4.
-        float vs[NV], vt[NV];
-        {
-            const float* gs = p.qs + qt_index(ph, slot, L);   // the group is one panel: L * 64 contiguous bytes
-            const float* gg = p.qg + qt_index(ph, slot, L);
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const bool on = valid && (i < NFULL || has_tail);
-                vs[i] = on ? __ldcs(gs + i * gstride) : 0.f;
-                vt[i] = on ? __ldcs(gg + i * gstride) : 0.f;
-            }
-        }
         // pass 1: e, partial row sums
         float zs = 0.f, zt = 0.f;
 #pragma unroll
@@ -100,16 +120,14 @@ __global__ void __launch_bounds__(kRowTThreads, 2) row_loss_t_kernel(RowLossTPar
             zs += vs[i];
             zt += vt[i];
         }
-        red[0][ph][s] = zs;
-        red[1][ph][s] = zt;
+        zs += __shfl_xor_sync(0xffffffffu, zs, 16);   // the warp's two phases
+        zt += __shfl_xor_sync(0xffffffffu, zt, 16);
+        if (lane_ < NS) { red[0][warp_][s] = zs; red[1][warp_][s] = zt; }
         __syncthreads();
         float rs = 1.f, rt = 1.f;
         if (mode == SSL_B200_ROWS_NORM) {
-            float a = 0.f, b = 0.f;
-#pragma unroll
-            for (int k = 0; k < NPH; ++k) { a += red[0][k][s]; b += red[1][k][s]; }
-            rs = 1.0f / (a + eps);
-            rt = 1.0f / (b + eps);
+            rs = 1.0f / (tree_sum<NWARP>(&red[0][0][s], NS) + eps);
+            rt = 1.0f / (tree_sum<NWARP>(&red[1][0][s], NS) + eps);
         }
         // pass 2: rows, loss terms, dL/drow; vs <- s, vt <- g
         float l1 = 0.f, kl = 0.f, dot = 0.f;
@@ -134,12 +152,12 @@ __global__ void __launch_bounds__(kRowTThreads, 2) row_loss_t_kernel(RowLossTPar
         if (valid) { l1_tot += (double)l1; kl_tot += (double)kl; }
         __syncthreads();            // every thread has read red (row sums) before it is reused
         if (p.want_grad) {
-            red[0][ph][s] = dot;
+            dot += __shfl_xor_sync(0xffffffffu, dot, 16);
+            if (lane_ < NS) red[0][warp_][s] = dot;
             __syncthreads();
             float dsum = 0.f;
             if (mode == SSL_B200_ROWS_NORM) {
-#pragma unroll
-                for (int k = 0; k < NPH; ++k) dsum += red[0][k][s];
+                dsum = tree_sum<NWARP>(&red[0][0][s], NS);
             }
             // pass 3: dL/dq = chain * s * (g - sum_m g_m s_m)   (EXP rows: chain * e * g)
             {
@@ -155,6 +173,7 @@ __global__ void __launch_bounds__(kRowTThreads, 2) row_loss_t_kernel(RowLossTPar
                     }
                 }
             }
+            fetch(g + gridDim.x);
             __syncthreads();
             // pass 4: weights of the out-of-area terms (similarity.cu:123-124: where the neighbour counts as
             // zero only the centre pixel gets 2*I*g).
@@ -228,6 +247,8 @@ __global__ void __launch_bounds__(kRowTThreads, 2) row_loss_t_kernel(RowLossTPar
                     for (int i = threadIdx.x; i < n_here * KW * KW; i += kRowTThreads) dst[i] = sW[i];
                 }
             }
+        } else {
+            fetch(g + gridDim.x);
         }
     }
     // block partials (fixed reduction tree) -> scratch
