@@ -182,7 +182,11 @@ __global__ void __launch_bounds__(kRowTThreads, 2) row_loss_t_kernel(RowLossTPar
             //  (b) wtab[slot][(a,b)] = sum of sG over the classes for which window offset (a,b) is out of area:
             //      sums over the column classes first (sR: whole row class out, sT: column b out), then over
             //      the row classes.  Rows of 16 slots are contiguous in wtab: written as one coalesced block.
+#ifdef SSLB_EXPERIMENT_NOPASS4   // timing experiment only: the row loss without the out-of-area weights
+            if (p.wtab && vs[0] == 123.456f) {
+#else
             if (p.wtab) {
+#endif
                 constexpr int U = P - K;
                 // (a) the 4K classes of one clipped dy (or dx) against all unclipped dx (dy) are sums of 2U+1 offsets in
                 //     a row (column) of the offset grid: one per phase; the 4K^2 corner classes are single offsets
