@@ -300,7 +300,11 @@ __device__ __forceinline__ void place_apply(const PlaneBwdParams& p, const int32
             place_offsets<Cfg>(kind, dy, lo_off, hi_off);
             place_batch<Cfg, NB>(A, f.packed[kind], f.val[kind], lo_off, hi_off, head);
             // columns with more than NB entries of a kind (dense masks): the rest, in batches of 4
+#ifdef SSLB_EXPERIMENT_NOOVERFLOW   // timing experiment only: entries beyond the prefetched NB are dropped
+            if (f.e0[kind] + NB < f.e1[kind] && f.val[kind][0] == 123.456f) {
+#else
             if (f.e0[kind] + NB < f.e1[kind]) {
+#endif
                 const float* gq = place_source<Cfg>(p, kind, dy, dx);
                 for (int e = f.e0[kind] + NB; e < f.e1[kind]; e += 4) {
                     int packed[4];
