@@ -516,7 +516,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(const __
     if (threadIdx.x < 32) tmem_alloc_512(&tmem_slot);   // warp 0 (the whole warp) allocates all 512 columns
     tmem_fence_before_sync();
 #endif
+#if !SSLB_BWD_TMEM
     for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::ACC_PITCH; i += blockDim.x) accT[i] = 0.f;
+#endif
     for (int i = threadIdx.x; i <= BC::RCOLS; i += blockDim.x) cols_s[i] = cols_g[i];
     {
         const uint32_t* cg = reinterpret_cast<const uint32_t*>(p.tile_cum + (long long)t * BC::RCOLS * BC::CUM_PITCH);
@@ -560,36 +562,47 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) ssg_plane_bwd_kernel(const __
     if (staged) dispatch(ent_s);
     else dispatch(ent_g);
 #if SSLB_BWD_TMEM
-    // the four quarter accumulators are added into the (zeroed) shared tile in quarter order, then TMEM is released
+    // Epilogue: every warp copies a third of its quarter's partial tile from TMEM into a staging area (the image
+    // tile, the placement buffers, accT and the lists are free now and contiguous), then each thread adds the four partials of
+    // its output elements in the fixed order (q0 + q1) + (q2 + q3) and writes the result.  TMEM is released in between.
+    constexpr int QS = 3 * Cfg::ROWS * BC::ACC_PITCH;              // floats of one staged partial tile
+    static_assert(4 * QS * sizeof(float) <= (Cfg::TILE_FLOATS + Cfg::NWP * BC::U_WORKER + QS) * sizeof(float) +
+                                                BC::LIST_SMEM * sizeof(int32_t) + BC::RCOLS * BC::CUM_PITCH,
+                  "the staging area of the epilogue is the kernel's whole dynamic shared memory (lists included)");
+    static_assert(Cfg::NWP % 4 == 0 && (3 * BC::TXB / 8) % (Cfg::NWP / 4) == 0, "columns split evenly over a quarter's warps");
+    float* S = tile;
     tmem_fence_before_sync();
     __syncthreads();
     tmem_fence_after_sync();
-    for (int q = 0; q < 4; ++q) {
-        if ((threadIdx.x >> 5) == q) {
-            const int r = threadIdx.x & 31;
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16);
-            for (int c = 0; c < 3; ++c)
-                for (int x = 0; x < BC::TXB; x += 8) {
-                    float v[8];
-                    tmem_ld8(ta + c * BC::TXB + x, v);
-                    float* dst = accT + (c * Cfg::ROWS + r) * BC::ACC_PITCH + x;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] += v[i];
-                }
+    {
+        const int w = threadIdx.x >> 5, r = threadIdx.x & 31, q = w & 3;
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int j = w >> 2; j < 3 * BC::TXB / 8; j += Cfg::NWP / 4) {
+            float v[8];
+            tmem_ld8(ta + 8 * j, v);
+            const int c = (8 * j) / BC::TXB, x = (8 * j) % BC::TXB;
+            float4* dst = reinterpret_cast<float4*>(S + q * QS + (c * Cfg::ROWS + r) * BC::ACC_PITCH + x);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
-        __syncthreads();
     }
     tmem_fence_before_sync();
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc_512(tmem_base);
+    // the factor 2 of d(t^2) is applied here, once
+    for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::TXB; i += blockDim.x) {
+        const int xo = i % BC::TXB, rr = (i / BC::TXB) % Cfg::ROWS, c = i / (BC::TXB * Cfg::ROWS);
+        const float* sp = S + (c * Cfg::ROWS + rr) * BC::ACC_PITCH + xo;
+        out[((long long)c * p.HT + Yb0 + rr) * p.WT + Xb0 + xo] = 2.f * ((sp[0] + sp[QS]) + (sp[2 * QS] + sp[3 * QS]));
+    }
 #else
     __syncthreads();
-#endif
     // the factor 2 of d(t^2) is applied here, once
     for (int i = threadIdx.x; i < 3 * Cfg::ROWS * BC::TXB; i += blockDim.x) {
         const int xo = i % BC::TXB, rr = (i / BC::TXB) % Cfg::ROWS, c = i / (BC::TXB * Cfg::ROWS);
         out[((long long)c * p.HT + Yb0 + rr) * p.WT + Xb0 + xo] = 2.f * accT[(c * Cfg::ROWS + rr) * BC::ACC_PITCH + xo];
     }
+#endif
 }
 
 template <typename Cfg>
