@@ -255,11 +255,10 @@ __device__ __forceinline__ void place_batch(float* A, const int (&packed)[NB], c
     for (int m = 0; m < NB; ++m)
         if (ok[m] && r0[m] > 0) cur[m] = A[r0[m] * 32];
 #pragma unroll
-    for (int m = 0; m < NB; ++m)
-        if (ok[m]) {
-            if (r0[m] > 0) A[r0[m] * 32] = cur[m] + val[m];
-            else head += val[m];
-        }
+    for (int m = 0; m < NB; ++m) {   // branch-free: val is zero for an empty slot
+        if (ok[m] && r0[m] > 0) A[r0[m] * 32] = cur[m] + val[m];
+        head += (ok[m] && r0[m] <= 0) ? val[m] : 0.f;
+    }
 #pragma unroll
     for (int m = 0; m < NB; ++m)
         if (ok[m] && r1[m] < Cfg::ROWS - 1) cur[m] = A[(r1[m] + 1) * 32];
