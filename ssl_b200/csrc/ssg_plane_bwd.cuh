@@ -214,14 +214,14 @@ __device__ __forceinline__ void place_fetch(const PlaneBwdParams& p, const int32
         place_offsets<Cfg>(kind, dy, lo_off, hi_off);
         // region rows whose run meets tile rows [0, ROWS)
         const int rr_lo = max(0, -hi_off), rr_hi = min(BC::RROWS - 1, Cfg::ROWS - 1 - lo_off);
+        // branch-free: the lists are read at a clamped column and the range is emptied afterwards (rr_lo and
+        // rr_hi + 1 always lie inside the cum row: |offsets| <= 2P + K < RROWS - ROWS)
         const bool ok = pcol >= 0 && pcol < BC::RCOLS && rr_lo <= rr_hi;
-        int e0 = 0, e1 = 0;
-        if (ok) {
-            const int base = cols[pcol];
-            const uint8_t* cc = cum + pcol * BC::CUM_PITCH;
-            e0 = base + cc[rr_lo];
-            e1 = base + cc[rr_hi + 1];
-        }
+        const int pc = min(max(pcol, 0), BC::RCOLS - 1);
+        const int base = cols[pc];
+        const uint8_t* cc = cum + pc * BC::CUM_PITCH;
+        const int e0 = ok ? base + cc[rr_lo] : 0;
+        const int e1 = ok ? base + cc[min(rr_hi, BC::RROWS - 1) + 1] : 0;
         f.e0[kind] = e0;
         f.e1[kind] = e1;
         const float* gq = place_source<Cfg>(p, kind, dy, dx);
