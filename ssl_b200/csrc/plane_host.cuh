@@ -271,7 +271,7 @@ inline int launch_plane_backward_cfg(const float* pad, int B, int H, int W, cons
         if (gcls)   // the fused step's row loss has written wtab already
             plane_wtab_kernel<Cfg><<<di.sm_count * 8, 128, 0, st>>>(gcls, lists.counts, l.cap,
                                                                    reinterpret_cast<float*>(ws + l.off_wtab));
-        plane_fold_kernel<Cfg><<<dim3(l.WT / 16, l.HT / 16, B), 256, 0, st>>>(fp);
+        plane_fold_kernel<Cfg, BG::NDXG><<<dim3(l.WT / 16, l.HT / 16, B), 256, 0, st>>>(fp);
         if (grad_out) plane_finish_kernel<Cfg><<<(int)((npx + 255) / 256), 256, 0, st>>>(fp);
     }
     return check_launch("plane_backward", 5);

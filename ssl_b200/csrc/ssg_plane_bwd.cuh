@@ -694,11 +694,25 @@ struct PlaneFinishParams {
 //   wsum(Y,X) = sum over the edge pixels p = (Y,X) - (a,b), |a|,|b| <= K, of wtab[p][(a,b)]   (the slots of the
 //               (16+2K)^2 pixels around the block are staged once)
 //   G(Y,X,c)  = sum of the dx-group partials + 2 * wsum * I(Y,X,c)        -> written over part 0
-template <typename Cfg>
+template <typename Cfg, int NPARTS>
 __global__ void __launch_bounds__(256) plane_fold_kernel(PlaneFinishParams p) {
     constexpr int P = Cfg::P, K = Cfg::K, KW = Cfg::KW, T = 16, R = T + 2 * K;
     __shared__ int32_t ss[R][R + 1];
     const int b = blockIdx.z, Y0 = blockIdx.y * T, X0 = blockIdx.x * T;
+    const int ty = threadIdx.x / T, tx = threadIdx.x % T;
+    const int Y = Y0 + ty, X = X0 + tx;
+    const long long plane = (long long)p.HT * p.WT;
+    const bool inside = Y < p.Hp && X < p.W + 2 * P;
+    // the partials and the image are independent of the slots: all 3 * NPARTS + 3 loads are in flight while the
+    // slot tile is staged
+    float part[3][NPARTS], img[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const long long o = ((long long)b * 3 + c) * plane + (long long)Y * p.WT + X;
+#pragma unroll
+        for (int k = 0; k < NPARTS; ++k) part[c][k] = p.gpart[(long long)k * p.B * 3 * plane + o];
+        img[c] = inside ? __ldg(p.pad + (((long long)b * 3 + c) * p.Hp + Y) * p.pitch + X) : 0.f;
+    }
     int any = 0;
     for (int i = threadIdx.x; i < R * R; i += 256) {
         const int ry = i / R, rx = i % R;
@@ -710,26 +724,29 @@ __global__ void __launch_bounds__(256) plane_fold_kernel(PlaneFinishParams p) {
         any |= slot >= 0;
     }
     any = __syncthreads_or(any);
-    const int ty = threadIdx.x / T, tx = threadIdx.x % T;
     float w = 0.f;
     if (any) {
-        // edge pixel at region (ty + K - a, tx + K - b) reaches this pixel with window offset (a, b)
+        // edge pixel at region (ty + K - a, tx + K - b) reaches this pixel with window offset (a, b); one partial sum
+        // per window column keeps the gathers of a window row independent of each other
+        float wcol[KW];
+#pragma unroll
+        for (int bb = 0; bb < KW; ++bb) wcol[bb] = 0.f;
         for (int a = -K; a <= K; ++a)
 #pragma unroll
             for (int bb = -K; bb <= K; ++bb) {
                 const int slot = ss[ty + K - a][tx + K - bb];
-                if (slot >= 0) w += p.wtab[(long long)slot * (KW * KW) + (a + K) * KW + bb + K];
+                if (slot >= 0) wcol[bb + K] += p.wtab[(long long)slot * (KW * KW) + (a + K) * KW + bb + K];
             }
+#pragma unroll
+        for (int bb = 0; bb < KW; ++bb) w += wcol[bb];
     }
-    const int Y = Y0 + ty, X = X0 + tx;
-    const long long plane = (long long)p.HT * p.WT;
-    const bool inside = Y < p.Hp && X < p.W + 2 * P;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const long long o = ((long long)b * 3 + c) * plane + (long long)Y * p.WT + X;
         float s = 0.f;
-        for (int part = 0; part < p.n_parts; ++part) s += p.gpart[(long long)part * p.B * 3 * plane + o];
-        if (inside) s = fmaf(2.f * w, __ldg(p.pad + (((long long)b * 3 + c) * p.Hp + Y) * p.pitch + X), s);
+#pragma unroll
+        for (int k = 0; k < NPARTS; ++k) s += part[c][k];
+        if (inside) s = fmaf(2.f * w, img[c], s);
         p.gpart[o] = s;
     }
 }
