@@ -60,19 +60,28 @@ __global__ void __launch_bounds__(kEoutThreads) plane_eout_kernel(PlaneFwdParams
     const int Wp = p.g.W + 2 * P;
     const long long plane = (long long)p.Hp * p.pitch;
     const float* img = p.pad + ((long long)(p.img_first + which) * p.g.B + b) * 3 * plane;
-    for (int i = threadIdx.x; i < ER * EC; i += blockDim.x) {
-        const int ry = i / EC, rx = i - ry * EC;
-        const int Y = Y0 + ry, X = X0 + rx;
-        float e = 0.f;
-        if (Y >= 0 && Y < p.Hp && X >= 0 && X < Wp) {
+    // four region elements per thread and step: 12 independent loads in flight (the block has only 64 threads)
+    constexpr int FU = 4;
+    for (int i0 = threadIdx.x; i0 < ER * EC; i0 += FU * kEoutThreads) {
+        float v[FU][3];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            const int i = i0 + u * kEoutThreads;
+            const int ry = i / EC, rx = i - ry * EC;
+            const int Y = Y0 + ry, X = X0 + rx;
+            const bool in = i < ER * EC && Y >= 0 && Y < p.Hp && X >= 0 && X < Wp;
             const float* q = img + (long long)Y * p.pitch + X;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v = __ldg(q + c * plane);
-                e = fmaf(v, v, e);
+            for (int c = 0; c < 3; ++c) v[u][c] = in ? __ldg(q + c * plane) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            const int i = i0 + u * kEoutThreads;
+            if (i < ER * EC) {
+                const int ry = i / EC, rx = i - ry * EC;
+                sE2[ry * EP + rx] = fmaf(v[u][2], v[u][2], fmaf(v[u][1], v[u][1], v[u][0] * v[u][0]));
             }
         }
-        sE2[ry * EP + rx] = e;
     }
     __syncthreads();
     float* eout = const_cast<float*>(which ? p.eout[1] : p.eout[0]);
