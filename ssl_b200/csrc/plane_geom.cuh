@@ -245,13 +245,16 @@ __global__ void __launch_bounds__(256) plane_units_emit_kernel(PlaneListParams p
     const int ksr = kSpreadRows > 0 ? kSpreadRows : 1;
     const int m = (n + ksr - 1) / ksr, nfull = n / m, part = n % m;
     const int gtot = ((n + 3) & ~3) / 4;
+    int rr = rank / m, cc = rank - rr * m;   // kept incrementally below: one division per lane, none per edge pixel
     for (int t = 0; t < n; ++t) {
         if (s_h[wib][t] != lane) continue;
-        const int rr = rank / m, cc = rank % m;
         const int f = cc * nfull + (cc < part ? cc : part) + rr;
+        // f < 4 * gtot: quotient and remainder by comparisons
+        const int fq = (f >= gtot) + (f >= 2 * gtot) + (f >= 3 * gtot), fr = f - fq * gtot;
         // kSpreadRows == 0: column-major order inside the unit (the entries of an image column are consecutive slots)
-        const int slot = kSpreadRows > 0 ? start + 4 * (f % gtot) + f / gtot : start + rank;
+        const int slot = kSpreadRows > 0 ? start + 4 * fr + fq : start + rank;
         ++rank;
+        if (++cc == m) { cc = 0; ++rr; }
         if (slot < p.capacity) {
             p.out.slot_pix[slot] = s_pix[wib][t];
             p.out.slot_rc[slot] = s_rc[wib][t];
