@@ -89,8 +89,6 @@ inline int launch_plane_lists(const float* mask, int mask_channels, int stride, 
     const int blocks = (g.n_units * 32 + 255) / 256;
     plane_units_count_kernel<<<blocks, 256, 0, st>>>(p);
     plane_units_scan_kernel<<<1, 1024, 0, st>>>(p);
-    static const int order_override = getenv("SSL_B200_SLOT_ORDER") ? atoi(getenv("SSL_B200_SLOT_ORDER")) : -1;   // experiment
-    if (order_override >= 0) spread = order_override;
     plane_units_emit_kernel<<<(g.n_units + 7) / 8, 256, 0, st>>>(p, srp, spread);
     return check_launch("plane_lists", n_launch);
 }
