@@ -94,7 +94,10 @@ struct PlaneBwdCfg {
     static constexpr int FULL_ROUNDS = Cfg::KS / Cfg::NWP;
     static constexpr bool SPLIT_LAST = Cfg::KS % Cfg::NWP == 1 && NCHB - 1 <= Cfg::NWP;
     static constexpr int N_ITEMS = SPLIT_LAST ? FULL_ROUNDS + 1 : (Cfg::KS + Cfg::NWP - 1) / Cfg::NWP;
-    static constexpr int NB = 8;                         // dL/dq values per kind prefetched into registers
+#ifndef SSLB_NB
+#define SSLB_NB 8
+#endif
+    static constexpr int NB = SSLB_NB;                   // dL/dq values per kind prefetched into registers
     static_assert((ACC_PITCH / 4) % 2 == 1, "accumulator rows must be float4 conflict-free");
     static_assert(G * 8 == 32 && Cfg::ROWS == 32, "one lane per (plane, u-column) when placing");
     static_assert(Cfg::NDXG <= 7, "dx-group dispatch");
