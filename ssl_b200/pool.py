@@ -15,7 +15,6 @@ that carry the edge mask along with LQ / GT.
 """
 from __future__ import annotations
 
-import ctypes
 import random
 from typing import List, Optional, Sequence, Tuple
 
