@@ -213,8 +213,25 @@ __device__ __forceinline__ void box_carry_reset(BoxCarry& c) {
     c.s8 = 0.f;
 }
 
-template <int LEN>
+template <int LEN, bool PREFIX_SUFFIX = true>
 __device__ __forceinline__ void box_last(const float (&cur)[8], BoxCarry& c, float (&out)[8]) {
+    if constexpr (PREFIX_SUFFIX && (LEN == 9 || LEN == 8)) {
+        // Windows of 8 or 9 over chunks of 8 (van Herk / Gil-Werman): a window that ends at column m of this chunk is
+        // a SUFFIX of the previous chunk plus the PREFIX 0..m of this one, so 7 + 7 additions build the prefix and
+        // suffix sums of a chunk and 8 more combine them -- 2.75 additions per output instead of 4, still nothing
+        // but sums of at most 9 non-negative terms.  c.w carries the previous chunk's suffix sums (zero at the start).
+        constexpr int SH = 9 - LEN;                  // the suffix of a LEN-window starts SH columns later
+        float pre[8];
+        pre[0] = cur[0];
+#pragma unroll
+        for (int m = 1; m < 8; ++m) pre[m] = pre[m - 1] + cur[m];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) out[m] = m + SH < 8 ? c.w[m + SH] + pre[m] : pre[m];
+        c.w[7] = cur[7];
+#pragma unroll
+        for (int m = 6; m >= 0; --m) c.w[m] = c.w[m + 1] + cur[m];
+        return;
+    }
     float w[16], s2[16], s4[16], s8[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { w[i] = c.w[i]; w[8 + i] = cur[i]; }
