@@ -244,30 +244,34 @@ __device__ __forceinline__ void place_fetch(const PlaneBwdParams& p, const int32
 template <typename Cfg, int NB>
 __device__ __forceinline__ void place_batch(float* A, const int (&packed)[NB], const float (&val)[NB], int lo_off,
                                             int hi_off, float& head) {
+    // An empty slot (packed = -1) decodes to region row 255, far beyond every run that can meet the tile (region rows
+    // are < RROWS <= 80 and the offsets lie in [-(2P + K), K]): all three range tests below fail for it by themselves.
+    static_assert(PlaneBwdCfg<Cfg>::RROWS + 2 * Cfg::P + Cfg::K < 255 - Cfg::ROWS, "row 255 must stay out of range");
     int r0[NB], r1[NB];
-    bool ok[NB];
+    bool in0[NB], in1[NB];
     float cur[NB];
 #pragma unroll
     for (int m = 0; m < NB; ++m) {
         const int rr = packed[m] & 255;
         r0[m] = rr + lo_off;
         r1[m] = rr + hi_off;
-        ok[m] = packed[m] >= 0;
+        in0[m] = (unsigned)(r0[m] - 1) < (unsigned)(Cfg::ROWS - 1);   // "+val" lands in rows 1 .. ROWS-1
+        in1[m] = (unsigned)r1[m] < (unsigned)(Cfg::ROWS - 1);         // "-val" lands in rows 1 .. ROWS-1 (r1 + 1)
     }
 #pragma unroll
     for (int m = 0; m < NB; ++m)
-        if (ok[m] && r0[m] > 0) cur[m] = A[r0[m] * 32];
+        if (in0[m]) cur[m] = A[r0[m] * 32];
 #pragma unroll
     for (int m = 0; m < NB; ++m) {   // branch-free: val is zero for an empty slot
-        if (ok[m] && r0[m] > 0) A[r0[m] * 32] = cur[m] + val[m];
-        head += (ok[m] && r0[m] <= 0) ? val[m] : 0.f;
+        if (in0[m]) A[r0[m] * 32] = cur[m] + val[m];
+        head += r0[m] <= 0 ? val[m] : 0.f;
     }
 #pragma unroll
     for (int m = 0; m < NB; ++m)
-        if (ok[m] && r1[m] < Cfg::ROWS - 1) cur[m] = A[(r1[m] + 1) * 32];
+        if (in1[m]) cur[m] = A[(r1[m] + 1) * 32];
 #pragma unroll
     for (int m = 0; m < NB; ++m)
-        if (ok[m] && r1[m] < Cfg::ROWS - 1) A[(r1[m] + 1) * 32] = cur[m] - val[m];
+        if (in1[m]) A[(r1[m] + 1) * 32] = cur[m] - val[m];
 }
 
 // All lanes of the worker call this (it contains warp barriers); lanes without a column (active == false:
