@@ -230,8 +230,9 @@ __device__ __forceinline__ void place_fetch(const PlaneBwdParams& p, const int32
         const float* gq = place_source<Cfg>(p, kind, dy, dx);
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
-            f.packed[kind][m] = e0 + m < e1 ? ent[e0 + m] : -1;
-            f.val[kind][m] = f.packed[kind][m] >= 0 ? SSLB_GQ(gq, f.packed[kind][m]) : 0.f;
+            const bool on = e0 + m < e1;   // list entries are never negative: one predicate serves both loads
+            f.packed[kind][m] = on ? ent[e0 + m] : -1;
+            f.val[kind][m] = on ? SSLB_GQ(gq, f.packed[kind][m]) : 0.f;
         }
     }
 }
@@ -317,8 +318,9 @@ __device__ __forceinline__ void place_apply(const PlaneBwdParams& p, const int32
                     float val[4];
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
-                        packed[m] = e + m < f.e1[kind] ? ent[e + m] : -1;
-                        val[m] = packed[m] >= 0 ? SSLB_GQ(gq, packed[m]) : 0.f;
+                        const bool on = e + m < f.e1[kind];
+                        packed[m] = on ? ent[e + m] : -1;
+                        val[m] = on ? SSLB_GQ(gq, packed[m]) : 0.f;
                     }
                     place_batch<Cfg, 4>(A, packed, val, lo_off, hi_off, head);
                 }
