@@ -29,8 +29,8 @@ namespace sslb {
 // with tcgen05.ld / tcgen05.st, on a datapath of its own: nothing of it goes through the shared-memory pipe that
 // bounds this kernel.  A warp reaches the 32 lanes of its own quarter (warp id mod 4) -- with lane = image row,
 // which is exactly how a worker holds its partial sums -- so the CTA keeps FOUR partial accumulator tiles, one per
-// quarter, each shared by the three workers whose warp id falls into it; they are added up (in quarter order)
-// once, at the end.  `#define SSLB_BWD_TMEM 0` builds the shared-memory accumulator of round 1 instead.
+// quarter, each shared by the three workers whose warp id falls into it; they are added up -- (q0 + q1) + (q2 + q3)
+// -- once, at the end (all warps stage their share of the partials, one barrier, sum at the output store).  `#define SSLB_BWD_TMEM 0` builds the shared-memory accumulator of round 1 instead.
 #ifndef SSLB_BWD_TMEM
 #define SSLB_BWD_TMEM 1
 #endif
