@@ -363,7 +363,7 @@ __device__ __forceinline__ void sweep_chunk_bwd(const float* tile, const float* 
         float cur[8];
         *reinterpret_cast<float4*>(&cur[0]) = up[0];
         *reinterpret_cast<float4*>(&cur[4]) = up[1];
-        box_last<len, false>(cur, carry[j], gs[j]);   // the pairwise tree: the prefix/suffix form costs this kernel registers
+        box_last<len>(cur, carry[j], gs[j]);
     });
     if (prime) return;  // the first chunk of an item only primes the tree (its outputs belong to the chunk before)
 #pragma unroll

@@ -221,12 +221,12 @@ __device__ __forceinline__ void box_last(const float (&cur)[8], BoxCarry& c, flo
         // suffix sums of a chunk and 8 more combine them -- 2.75 additions per output instead of 4, still nothing
         // but sums of at most 9 non-negative terms.  c.w carries the previous chunk's suffix sums (zero at the start).
         constexpr int SH = 9 - LEN;                  // the suffix of a LEN-window starts SH columns later
-        float pre[8];
-        pre[0] = cur[0];
+        float pre = 0.f;                             // running prefix: a carried suffix sum is dead once it is used
 #pragma unroll
-        for (int m = 1; m < 8; ++m) pre[m] = pre[m - 1] + cur[m];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) out[m] = m + SH < 8 ? c.w[m + SH] + pre[m] : pre[m];
+        for (int m = 0; m < 8; ++m) {
+            pre = m == 0 ? cur[0] : pre + cur[m];
+            out[m] = m + SH < 8 ? c.w[m + SH] + pre : pre;
+        }
         c.w[7] = cur[7];
 #pragma unroll
         for (int m = 6; m >= 0; --m) c.w[m] = c.w[m + 1] + cur[m];
