@@ -338,13 +338,9 @@ __device__ __forceinline__ void place_apply(const PlaneBwdParams& p, const int32
         for (int i = 0; i < 8; ++i) v[i] = A[(i0 + i) * 32];
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; i += 4) {
-            const float s01 = v[i] + v[i + 1], s012 = s01 + v[i + 2], s0123 = s012 + v[i + 3];
-            Bc[(i0 + i) * BC::UB_PITCH] = v[i] + run;
-            Bc[(i0 + i + 1) * BC::UB_PITCH] = s01 + run;
-            Bc[(i0 + i + 2) * BC::UB_PITCH] = s012 + run;
-            run = s0123 + run;
-            Bc[(i0 + i + 3) * BC::UB_PITCH] = run;
+        for (int i = 0; i < 8; ++i) {
+            run += v[i];
+            Bc[(i0 + i) * BC::UB_PITCH] = run;
         }
     }
     __syncwarp();
